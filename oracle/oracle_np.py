@@ -1,0 +1,566 @@
+"""numpy restatement of the DeepMerge region-merging hot path (TEST INFRASTRUCTURE).
+
+Every function cites the reference file:line it follows, or says "spec" when the
+reference has no code for the stage (parity unpinned there).
+Nothing in ``deepmerge_b200`` imports this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+M32 = np.uint64(0xFFFFFFFF)
+NODATA = -1
+
+# --------------------------------------------------------------------------- #
+# counter-based hashing shared (bit-for-bit) with csrc/synth.cu
+# --------------------------------------------------------------------------- #
+
+
+def _u64(x):
+    return np.asarray(x).astype(np.uint64) & M32
+
+
+def mix32(x):
+    """lowbias32 integer finaliser on 32-bit lanes held in uint64."""
+    x = _u64(x)
+    x = x ^ (x >> np.uint64(16))
+    x = (x * np.uint64(0x7FEB352D)) & M32
+    x = x ^ (x >> np.uint64(15))
+    x = (x * np.uint64(0x846CA68B)) & M32
+    x = x ^ (x >> np.uint64(16))
+    return x
+
+
+def hash32(seed, a, b=0, c=0):
+    h = mix32((_u64(c) + np.uint64(0xC2B2AE35)) & M32)
+    h = mix32(((_u64(b) + np.uint64(0x85EBCA6B)) & M32) ^ h)
+    h = mix32(((_u64(a) + np.uint64(0x9E3779B9)) & M32) ^ h)
+    return mix32(_u64(seed) ^ h)
+
+
+# --------------------------------------------------------------------------- #
+# synthetic scene; spec, no reference code
+# --------------------------------------------------------------------------- #
+
+
+def grid_pitch(H, W, R):
+    return max(1, int(round((H * W / max(R, 1)) ** 0.5)))
+
+
+def voronoi_seeds(H, W, g, seed):
+    """One jittered seed per g x g cell.  Returns (sx, sy) int64 [ncy, ncx]."""
+    ncx, ncy = -(-W // g), -(-H // g)
+    cy, cx = np.meshgrid(np.arange(ncy), np.arange(ncx), indexing="ij")
+    sx = cx * g + (hash32(seed, cx, cy, 0) % np.uint64(g)).astype(np.int64)
+    sy = cy * g + (hash32(seed, cx, cy, 1) % np.uint64(g)).astype(np.int64)
+    return sx, sy
+
+
+def voronoi_at(xs, ys, g, sx, sy):
+    """Id (cy*ncx+cx) of the nearest seed among the 3x3 neighbouring cells;
+    ties go to the lower id.  xs, ys broadcastable int arrays."""
+    ncy, ncx = sx.shape
+    xs = np.asarray(xs, np.int64)
+    ys = np.asarray(ys, np.int64)
+    cx0 = np.clip(xs // g, 0, ncx - 1)
+    cy0 = np.clip(ys // g, 0, ncy - 1)
+    best_d = np.full(np.broadcast(xs, ys).shape, np.iinfo(np.int64).max, np.int64)
+    best_id = np.zeros(best_d.shape, np.int64)
+    for dy in (-1, 0, 1):           # ascending id order => strict '<' keeps lower id on ties
+        for dx in (-1, 0, 1):
+            cx, cy = cx0 + dx, cy0 + dy
+            ok = (cx >= 0) & (cx < ncx) & (cy >= 0) & (cy < ncy)
+            cxc, cyc = np.clip(cx, 0, ncx - 1), np.clip(cy, 0, ncy - 1)
+            d = (xs - sx[cyc, cxc]) ** 2 + (ys - sy[cyc, cxc]) ** 2
+            better = ok & (d < best_d)
+            best_d = np.where(better, d, best_d)
+            best_id = np.where(better, cyc * ncx + cxc, best_id)
+    return best_id
+
+
+def synth_labels(H, W, R, seed=1234, rows=None):
+    """int32 [H,W] jittered-grid Voronoi label raster with ids in [0, ncx*ncy)."""
+    g = grid_pitch(H, W, R)
+    sx, sy = voronoi_seeds(H, W, g, seed)
+    y0, y1 = (0, H) if rows is None else rows
+    out = np.empty((y1 - y0, W), np.int32)
+    xs = np.arange(W)[None, :]
+    step = max(1, (1 << 22) // max(W, 1))
+    for a in range(y0, y1, step):
+        b = min(y1, a + step)
+        out[a - y0:b - y0] = voronoi_at(xs, np.arange(a, b)[:, None], g, sx, sy)
+    return out, sx.size
+
+
+def synth_region_objects(H, W, R, seed=1234):
+    """Ground-truth object of each region = coarse (pitch 4g) Voronoi cell of its seed."""
+    g = grid_pitch(H, W, R)
+    sx, sy = voronoi_seeds(H, W, g, seed)
+    G = 4 * g
+    ox, oy = voronoi_seeds(H, W, G, seed + 1)
+    obj = voronoi_at(sx.ravel(), sy.ravel(), G, ox, oy)
+    return obj.astype(np.int32), ox.size
+
+
+def synth_image(labels, region_obj, C, seed=1234, y0=0):
+    """uint8 [H,W,C]: object colour + region offset in [-4,4] + pixel noise in [-8,8]."""
+    H, W = labels.shape
+    lab = labels.astype(np.int64)
+    ok = lab >= 0
+    labc = np.where(ok, lab, 0)
+    obj = region_obj[labc].astype(np.int64)
+    yy, xx = np.meshgrid(np.arange(y0, y0 + H), np.arange(W), indexing="ij")
+    pix = (yy * W + xx) & 0xFFFFFFFF
+    out = np.empty((H, W, C), np.uint8)
+    for c in range(C):
+        col = 32 + (hash32(seed + 2, obj, c) % np.uint64(192)).astype(np.int64)
+        off = (hash32(seed + 3, labc, c) % np.uint64(9)).astype(np.int64) - 4
+        noi = (hash32(seed + 4, pix, c) % np.uint64(17)).astype(np.int64) - 8
+        v = np.clip(col + off + noi, 0, 255)
+        out[..., c] = np.where(ok, v, 0)
+    return out
+
+
+def synth_points(H, W, R, P=4, seed=1234):
+    """P sample points per grid cell around its seed (point 0 at the seed, clamped
+    into the image).  Returns xs, ys int32 [ncells*P] in cell-major, k-minor order."""
+    g = grid_pitch(H, W, R)
+    sx, sy = voronoi_seeds(H, W, g, seed)
+    r = np.arange(sx.size)
+    span = g // 2 + 1
+    xs = np.empty((sx.size, P), np.int64)
+    ys = np.empty((sx.size, P), np.int64)
+    for k in range(P):
+        if k == 0:
+            dx = dy = 0
+        else:
+            dx = (hash32(seed + 5, r, k, 0) % np.uint64(span)).astype(np.int64) - g // 4
+            dy = (hash32(seed + 5, r, k, 1) % np.uint64(span)).astype(np.int64) - g // 4
+        xs[:, k] = np.clip(sx.ravel() + dx, 0, W - 1)
+        ys[:, k] = np.clip(sy.ravel() + dy, 0, H - 1)
+    return xs.ravel().astype(np.int32), ys.ravel().astype(np.int32)
+
+
+def synth_feats(point_obj, D=100, seed=1234):
+    """fp32 [N,D] = object centre (triangular, sd 1.63) + point noise / 128.  Built from
+    integers so it is exact in fp32 and identical on CPU and GPU."""
+    N = point_obj.shape[0]
+    i = np.arange(N, dtype=np.int64)[:, None]
+    d = np.arange(D, dtype=np.int64)[None, :]
+    o = point_obj.astype(np.int64)[:, None]
+    hc = hash32(seed + 6, o, d)
+    hn = hash32(seed + 7, i, d)
+    ci = (hc & np.uint64(0xFFFF)).astype(np.int64) + (hc >> np.uint64(16)).astype(np.int64) - 65535
+    ni = (hn & np.uint64(0xFFFF)).astype(np.int64) + (hn >> np.uint64(16)).astype(np.int64) - 65535
+    return ((ci * 128 + ni).astype(np.float32) * np.float32(1.0 / 2097152.0)).astype(np.float32)
+
+
+def synth_scene(H, W, R, C=4, P=4, D=100, seed=1234):
+    labels, nreg = synth_labels(H, W, R, seed)
+    region_obj, nobj = synth_region_objects(H, W, R, seed)
+    image = synth_image(labels, region_obj, C, seed)
+    xs, ys = synth_points(H, W, R, P, seed)
+    rop = labels[ys, xs].astype(np.int32)
+    feats = synth_feats(region_obj[rop], D, seed)
+    return dict(labels=labels, n_regions=nreg, region_obj=region_obj, n_objects=nobj, image=image,
+                xs=xs, ys=ys, region_of_point=rop, feats=feats)
+
+
+# --------------------------------------------------------------------------- #
+# R1: region adjacency graph
+# --------------------------------------------------------------------------- #
+
+
+def pack_keys(a, b):
+    a = np.asarray(a, np.int64)
+    b = np.asarray(b, np.int64)
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    return (lo.astype(np.uint64) << np.uint64(32)) | hi.astype(np.uint64)
+
+
+def unpack_keys(keys):
+    keys = np.asarray(keys, np.uint64)
+    return (keys >> np.uint64(32)).astype(np.int64), (keys & M32).astype(np.int64)
+
+
+def edges_from_lines(left_fid, right_fid):
+    """Vector form, MyUtils2.py:177-193: keep rows in file order, drop a row when either
+    side is -1 (:184-186); not canonicalised, duplicates kept.  Returns kept row indices
+    (the line FIDs), left ids, right ids."""
+    left = np.asarray(left_fid, np.int64)
+    right = np.asarray(right_fid, np.int64)
+    keep = ~((left == -1) | (right == -1))
+    fid = np.nonzero(keep)[0]
+    return fid, left[keep], right[keep]
+
+
+def neighbours_from_join(join_field, self_id):
+    """MyUtils.py:110-114: comma list of neighbour ids including self; self removed."""
+    ids = [int(t) for t in join_field.split(",")]
+    ids.remove(self_id)
+    return ids
+
+
+def membership_csr(point_id_fields, sep=" "):
+    """ExtractFeatures.py:175-179 / MyUtils1.py:266-272: per-polygon 'PointID' string of
+    separator-joined point FIDs -> CSR (offsets int64 [R+1], point_ids int32 [N])."""
+    offsets = np.zeros(len(point_id_fields) + 1, np.int64)
+    ids = []
+    for r, f in enumerate(point_id_fields):
+        toks = [int(t) for t in f.split(sep)] if f != "" else []
+        ids.extend(toks)
+        offsets[r + 1] = len(ids)
+    return offsets, np.asarray(ids, np.int32)
+
+
+def build_rag(labels, n_regions, top_border=True, bottom_border=True, own_rows=None):
+    """Raster form of R1 (spec; unpinned by the reference).
+
+    labels int32 [H,W], >=0 valid, <0 nodata.  4-adjacency.  Returns
+      keys  uint64 [E]  sorted unique (min<<32)|max over differing valid neighbour pairs,
+      blen  uint32 [E]  number of straddling pixel pairs,
+      area  int64 [R]   pixel count,
+      perim int64 [R]   pixel sides facing another label, nodata or the image border.
+
+    ``own_rows``/``top_border``/``bottom_border`` describe a row tile of a larger scene:
+    the tile owns rows [0, own_rows); any further rows are a halo (only looked at as the
+    lower neighbour of the last owned row and never counted themselves).
+    """
+    L = np.asarray(labels, np.int32)
+    H, W = L.shape
+    own = H if own_rows is None else own_rows
+    R = n_regions
+    Lo = L[:own]
+    valid = Lo >= 0
+    area = np.bincount(Lo[valid].astype(np.int64), minlength=R).astype(np.int64)
+    a, b = Lo[:, :-1], Lo[:, 1:]
+    mh = (a != b) & (a >= 0) & (b >= 0)
+    kh = pack_keys(a[mh], b[mh])
+    up, dn = L[:min(own, H - 1)], L[1:min(own, H - 1) + 1]
+    mv = (up != dn) & (up >= 0) & (dn >= 0)
+    kv = pack_keys(up[mv], dn[mv])
+    keys, counts = np.unique(np.concatenate([kh, kv]), return_counts=True)
+    # perimeter, pair based so that it decomposes over row tiles: the tile that owns a
+    # pixel pair counts the side for BOTH pixels; image-border sides are added per tile.
+    perim = np.zeros(R, np.int64)
+
+    def add(lab):
+        lab = lab[lab >= 0].astype(np.int64)
+        perim[:] += np.bincount(lab, minlength=R)
+
+    dh = a != b
+    add(a[dh]); add(b[dh])
+    dv = up != dn
+    add(up[dv]); add(dn[dv])
+    add(Lo[:, 0]); add(Lo[:, W - 1])
+    if top_border:
+        add(Lo[0])
+    if bottom_border and own == H:
+        add(Lo[own - 1])
+    return keys, counts.astype(np.uint32), area, perim
+
+
+def perimeter_by_sides(labels, n_regions):
+    """Independent definition for a whole image: every valid pixel looks at its 4 sides
+    and counts those facing another label, nodata or the image border."""
+    L = np.asarray(labels, np.int32)
+    P = np.full((L.shape[0] + 2, L.shape[1] + 2), -2, np.int32)
+    P[1:-1, 1:-1] = L
+    perim = np.zeros(n_regions, np.int64)
+    for sl in (P[1:-1, :-2], P[1:-1, 2:], P[:-2, 1:-1], P[2:, 1:-1]):
+        m = (sl != L) & (L >= 0)
+        perim += np.bincount(L[m].astype(np.int64), minlength=n_regions)
+    return perim
+
+
+# --------------------------------------------------------------------------- #
+# pooling
+# --------------------------------------------------------------------------- #
+
+
+def pool_bands(labels, image, n_regions):
+    """Per-region band sums and sums of squares, exact integers (spec; the reference reads
+    mean0-2/std0-2 from attribute tables, MyUtils1.py:79-114, formulas not in the repo)."""
+    L = np.asarray(labels).ravel().astype(np.int64)
+    ok = L >= 0
+    C = image.shape[-1]
+    img = image.reshape(-1, C)
+    s = np.zeros((n_regions, C), np.uint64)
+    q = np.zeros((n_regions, C), np.uint64)
+    for c in range(C):
+        v = img[ok, c].astype(np.float64)
+        sc = np.bincount(L[ok], weights=v, minlength=n_regions)
+        qc = np.bincount(L[ok], weights=v * v, minlength=n_regions)
+        assert qc.max(initial=0) < 2 ** 53
+        s[:, c] = sc.astype(np.uint64)
+        q[:, c] = qc.astype(np.uint64)
+    return s, q
+
+
+def csr_from_region_of_point(region_of_point, n_regions):
+    """Group point ids by region, ascending point id inside a region (the order a
+    'PointID' field lists them in the synthetic scenes)."""
+    rop = np.asarray(region_of_point, np.int64)
+    ok = rop >= 0
+    order = np.argsort(np.where(ok, rop, n_regions), kind="stable")
+    order = order[: int(ok.sum())]
+    counts = np.bincount(rop[ok], minlength=n_regions)
+    offsets = np.zeros(n_regions + 1, np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    return offsets, order.astype(np.int32)
+
+
+def pool_points_csr(offsets, point_ids, feats):
+    """Region pooling, ExtractFeatures.py:188-212: rows gathered in PointID order and
+    reduced with np.mean(axis=0), i.e. sequential fp32 row accumulation then one fp32
+    division by n.  Returns (sum fp32 [R,D], cnt int32 [R], mean fp32 [R,D]); a region
+    with no points has sum = mean = 0 (the reference would raise on int(''))."""
+    offsets = np.asarray(offsets, np.int64)
+    R = offsets.shape[0] - 1
+    D = feats.shape[1]
+    cnt = np.diff(offsets)
+    acc = np.zeros((R, D), np.float32)
+    for k in range(int(cnt.max(initial=0))):
+        rows = np.nonzero(cnt > k)[0]
+        acc[rows] = acc[rows] + feats[point_ids[offsets[rows] + k]].astype(np.float32)
+    return acc, cnt.astype(np.int32), region_mean(acc, cnt)
+
+
+def region_mean(sum_, cnt):
+    c = np.maximum(np.asarray(cnt), 1).astype(np.float32)[:, None]
+    return (sum_.astype(np.float32) / c).astype(np.float32)
+
+
+def pool_dense(labels, emb, n_regions):
+    """Per-pixel embedding pooling (north-star raster form of R5): sum and count of the
+    embedding of every valid pixel per region; float64 accumulation (tolerance oracle)."""
+    L = np.asarray(labels).ravel().astype(np.int64)
+    ok = L >= 0
+    D = emb.shape[-1]
+    e = emb.reshape(-1, D)[ok].astype(np.float64)
+    s = np.zeros((n_regions, D), np.float64)
+    np.add.at(s, L[ok], e)
+    cnt = np.bincount(L[ok], minlength=n_regions)
+    return s, cnt.astype(np.int64)
+
+
+# --------------------------------------------------------------------------- #
+# scoring
+# --------------------------------------------------------------------------- #
+
+
+def euclidean_distance(X, Y):
+    """ExtractFeatures.py:119-147 restated: D[i,j]=sqrt(max(0,|X_i|^2+|Y_j|^2-2 X_i.Y_j))."""
+    X2 = np.sum(X ** 2, axis=1)
+    Y2 = np.sum(Y ** 2, axis=1)
+    D = X2[:, None] + Y2[None, :] - 2 * np.dot(X, Y.T)
+    D[D < 0] = 0
+    return np.sqrt(D)
+
+
+def score_l2(mean, keys):
+    """R6 for every edge: the reference's expanded formula, fp32, one (lo,hi) pair per row."""
+    lo, hi = unpack_keys(keys)
+    X = mean[lo].astype(np.float32)
+    Y = mean[hi].astype(np.float32)
+    D = np.sum(X * X, axis=1) + np.sum(Y * Y, axis=1) - np.float32(2) * np.einsum("ij,ij->i", X, Y)
+    D = np.maximum(D, np.float32(0))
+    return np.sqrt(D).astype(np.float32)
+
+
+def score_l2_f64(mean, keys):
+    """float64 direct-difference distance: the ground truth the fp32 tolerance refers to."""
+    lo, hi = unpack_keys(keys)
+    d = mean[lo].astype(np.float64) - mean[hi].astype(np.float64)
+    return np.sqrt(np.sum(d * d, axis=1))
+
+
+def l2_abs_tolerance(mean, keys, rel=1e-3):
+    """|score_gpu - score_f64| bound.  The expanded form cancels:
+    its error in D=d^2 is ~eps*(|x|^2+|y|^2), so in d it is min(that/d, sqrt(that))."""
+    lo, hi = unpack_keys(keys)
+    m = mean.astype(np.float64)
+    scale = np.sum(m[lo] ** 2, 1) + np.sum(m[hi] ** 2, 1)
+    d = score_l2_f64(mean, keys)
+    errD = 64 * np.finfo(np.float32).eps * scale
+    return rel * d + np.minimum(errD / np.maximum(d, 1e-30), np.sqrt(errD))
+
+
+def leaky_relu(x, slope=0.01):
+    return np.where(x >= 0, x, x * np.float32(slope)).astype(np.float32)
+
+
+def mlp_forward(x, W1, b1, W2, b2, W3, b3):
+    """Nets.py:28-35: three Linear + leaky_relu(0.01); returns (fc3_map, fc2_map)."""
+    h1 = leaky_relu(x.astype(np.float32) @ W1.T + b1)
+    h2 = leaky_relu(h1 @ W2.T + b2)
+    o = leaky_relu(h2 @ W3.T + b3)
+    return o, h2
+
+
+def pair_features(mean, keys):
+    """Pair-MLP input (spec R8): concat(mean[lo], mean[hi]) with lo<hi canonical."""
+    lo, hi = unpack_keys(keys)
+    return np.concatenate([mean[lo], mean[hi]], axis=1).astype(np.float32)
+
+
+def bf16_round(x):
+    """Round-to-nearest-even fp32 -> bf16 -> fp32 (what the tcgen05 path feeds the MMA)."""
+    u = np.asarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + np.uint64(0x7FFF) + ((u >> np.uint64(16)) & np.uint64(1))) >> np.uint64(16)) << np.uint64(16)
+    return (r & M32).astype(np.uint32).view(np.float32)
+
+
+def mlp_forward_bf16(x, W1, b1, W2, b2, W3, b3):
+    """Same network with every GEMM operand rounded to bf16 and fp32 accumulation: the
+    arithmetic dm_score_mlp_bf16 performs (up to fp32 summation order)."""
+    r = bf16_round
+    h1 = leaky_relu(r(x) @ r(W1).T + b1)
+    h2 = leaky_relu(r(h1) @ r(W2).T + b2)
+    o = leaky_relu(r(h2) @ r(W3).T + b3)
+    return o, h2
+
+
+def contrastive_loss(a, b, flag, margin):
+    """Losses.py:34-38 forward and its analytic gradients (R11)."""
+    a = a.astype(np.float32)
+    b = b.astype(np.float32)
+    f = flag.astype(np.float32)
+    d = np.sum((a - b) ** 2, axis=1)
+    losses = f * d + (1 - f) * np.maximum(np.float32(margin) - d, 0)
+    B = a.shape[0]
+    coef = (f - (1 - f) * (d < margin)).astype(np.float32)
+    ga = (np.float32(2.0 / B) * coef)[:, None] * (a - b)
+    return np.float32(losses.mean()), ga.astype(np.float32), (-ga).astype(np.float32)
+
+
+# --------------------------------------------------------------------------- #
+# R9: merge loop (spec)
+# --------------------------------------------------------------------------- #
+
+
+def union_find_min_root(n, u, v):
+    """Connected components over edges (u,v); every node gets the minimum id of its
+    component.  Plain union-find with path halving; union by smaller id."""
+    parent = np.arange(n, dtype=np.int64)
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    for a, b in zip(np.asarray(u).tolist(), np.asarray(v).tolist()):
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            if ra < rb:
+                parent[rb] = ra
+            else:
+                parent[ra] = rb
+    for x in range(n):
+        parent[x] = find(x)
+    return parent
+
+
+def min_root_propagate(n, u, v):
+    """Vectorised alternative (min-label propagation + pointer jumping); used for big
+    graphs and as an independent cross-check of union_find_min_root."""
+    root = np.arange(n, dtype=np.int64)
+    u = np.asarray(u, np.int64)
+    v = np.asarray(v, np.int64)
+    while True:
+        ru, rv = root[u], root[v]
+        m = np.minimum(ru, rv)
+        new = root.copy()
+        np.minimum.at(new, ru, m)
+        np.minimum.at(new, rv, m)
+        while True:
+            nn = new[new]
+            if np.array_equal(nn, new):
+                break
+            new = nn
+        if np.array_equal(new, root):
+            return root
+        root = new
+
+
+def merge_graph(sum_, cnt, area, perim, keys, blen, tau=None, mlp=None, max_rounds=64,
+                components=min_root_propagate):
+    """Iterative merge loop, spec SURVEY.md section 8(a) R9.
+
+    round: score live edges (L2: ExtractFeatures.py:119-147; MLP: Nets.py:28-35) ->
+    select (s<tau | argmax(o)==1) -> stop if none or max_rounds -> union-find, root = min
+    id -> merged sum (ascending member id, fp32 sequential), cnt, area,
+    perimeter - 2*internal boundary -> re-key, drop self loops, sort+unique, sum boundary.
+    Returns dict(root, rounds, merges, sum, cnt, area, perim, keys, blen, scores)."""
+    R = cnt.shape[0]
+    sum_ = sum_.astype(np.float32).copy()
+    cnt = cnt.astype(np.int64).copy()
+    area = area.astype(np.int64).copy()
+    perim = perim.astype(np.int64).copy()
+    keys = np.asarray(keys, np.uint64).copy()
+    blen = blen.astype(np.int64).copy()
+    root = np.arange(R, dtype=np.int64)
+    rounds = merges = 0
+    while True:
+        mean = region_mean(sum_, cnt)
+        if mlp is not None:
+            o, _ = mlp_forward(pair_features(mean, keys), *mlp)
+            scores = o
+            sel = o[:, 1] > o[:, 0] if len(keys) else np.zeros(0, bool)
+        else:
+            scores = score_l2(mean, keys)
+            sel = scores < np.float32(tau)
+        if rounds == max_rounds or not sel.any():
+            break
+        rounds += 1
+        lo, hi = unpack_keys(keys)
+        comp = components(R, lo[sel], hi[sel])          # comp[x] = min id of x's component
+        live = root == np.arange(R)
+        moved = np.nonzero(live & (comp != np.arange(R)))[0]   # ascending member id
+        merges += moved.size
+        order = np.argsort(comp[moved], kind="stable")
+        mv, tg = moved[order], comp[moved][order]
+        # sequential fp32 accumulation into the root, members in ascending id
+        starts = np.r_[0, np.nonzero(np.diff(tg))[0] + 1] if mv.size else np.zeros(0, np.int64)
+        lens = np.diff(np.r_[starts, mv.size])
+        for k in range(int(lens.max(initial=0))):
+            s = starts[lens > k] + k
+            sum_[tg[s]] = sum_[tg[s]] + sum_[mv[s]]
+        np.add.at(cnt, tg, cnt[mv])
+        np.add.at(area, tg, area[mv])
+        np.add.at(perim, tg, perim[mv])
+        nlo, nhi = comp[lo], comp[hi]
+        loop = nlo == nhi
+        np.add.at(perim, nlo[loop], -2 * blen[loop])
+        nk = pack_keys(nlo[~loop], nhi[~loop])
+        keys, inv = np.unique(nk, return_inverse=True)
+        blen = np.bincount(inv, weights=blen[~loop].astype(np.float64), minlength=keys.size).astype(np.int64)
+        root = comp[root]
+    return dict(root=root.astype(np.int32), rounds=rounds, merges=merges, sum=sum_, cnt=cnt.astype(np.int32),
+                area=area, perim=perim, keys=keys, blen=blen.astype(np.uint32), scores=scores)
+
+
+def relabel(labels, root):
+    """labels'[p] = root[labels[p]]; nodata (<0) pixels are kept."""
+    L = np.asarray(labels)
+    return np.where(L >= 0, root[np.where(L >= 0, L, 0)], L).astype(np.int32)
+
+
+def compact_roots(root):
+    """Optional compaction: roots -> 0..R'-1 in ascending root order."""
+    roots = np.unique(root)
+    lut = np.zeros(root.shape[0], np.int32)
+    lut[roots] = np.arange(roots.size, dtype=np.int32)
+    return lut[root], roots.size
+
+
+def merge_scene(labels, n_regions, region_of_point, feats, tau=None, mlp=None, max_rounds=64):
+    """End to end on one raster: RAG -> point pooling -> score -> merge loop -> relabel."""
+    keys, blen, area, perim = build_rag(labels, n_regions)
+    off, ids = csr_from_region_of_point(region_of_point, n_regions)
+    s, cnt, _ = pool_points_csr(off, ids, feats)
+    g = merge_graph(s, cnt, area, perim, keys, blen, tau=tau, mlp=mlp, max_rounds=max_rounds)
+    g["labels"] = relabel(labels, g["root"])
+    g["keys0"], g["blen0"], g["area0"], g["perim0"] = keys, blen, area, perim
+    return g
