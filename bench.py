@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the region-merging hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step = one end-to-end pass (RAG + band pooling -> point pooling -> L2 edge scoring ->
+iterative union-find merge -> relabel) over the synthetic scene of SURVEY.md section 8(d).
+N=1 workload: BASELINE.json configs[1] (10k x 10k, 4 bands, ~100k segments).  Prints ONE
+JSON line (rank 0).  `value` = Mpx/s with inputs resident in HBM; `e2e` = the same through
+the public API with HOST buffers (H2D of labels/image/points/embeddings and D2H of the label
+map inside the timed region); `roofline` = the fused RAG+pool raster kernel against the
+measured HBM peak; `cpu_baseline` = the oracle port timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CFG = dict(H=10000, W=10000, R=100000, C=4, P=4, D=100, tau=0.5, seed=1234)
+WORKLOAD = "configs[1]: 10k x 10k 4-band synthetic scene, ~100k segments, single B200 RAG+pool+score+merge"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample of the same workload
+# ----------------------------------------------------------------------------------------------
+def cpu_sample_dims(cfg, side):
+    """A side x side crop-equivalent of the workload: same region pitch, bands, P and D."""
+    scale = (side * side) / (cfg["H"] * cfg["W"])
+    return dict(cfg, H=side, W=side, R=max(4, int(round(cfg["R"] * scale))))
+
+
+def run_cpu_port(cfg, steps=1, warmup=0):
+    """Times oracle_np.merge_scene + band pooling (numpy, 1 thread) on the given scene."""
+    from oracle import oracle_np as o
+    sc = o.synth_scene(cfg["H"], cfg["W"], cfg["R"], C=cfg["C"], P=cfg["P"], D=cfg["D"], seed=cfg["seed"])
+    times = []
+    res = None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        res = o.merge_scene(sc["labels"], sc["n_regions"], sc["region_of_point"], sc["feats"], tau=cfg["tau"])
+        o.pool_bands(sc["labels"], sc["image"], sc["n_regions"])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return float(np.mean(times)), res, sc
+
+
+def reference_arm(args):
+    cfg = cpu_sample_dims(CFG, args.cpu_side)
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), min(args.warmup, 1)
+    sec, res, sc = run_cpu_port(cfg, steps=steps, warmup=warmup)
+    mpx = cfg["H"] * cfg["W"] / sec / 1e6
+    sample = f"{cfg['H']}x{cfg['W']} scene at the workload's region pitch ({sc['n_regions']} segments), {cfg['C']} bands"
+    line = {
+        "impl": "reference", "metric": "megapixels/sec end-to-end (RAG+pool+score+merge+relabel)", "value": mpx,
+        "unit": "Mpx/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/u8 index + fp32 scores",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": mpx, "unit": "Mpx/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": mpx, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "merged_edges_per_s": res["merges"] / sec,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from deepmerge_b200 import MergeEngine, _lib
+    from deepmerge_b200.raster import _p, _stream
+    from deepmerge_b200.synth import synth_scene
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from deepmerge_b200.sharded import bench_sharded
+        return bench_sharded(args, CFG, WORKLOAD, dist, dev, ClockSampler, measured_peaks)
+
+    L = _lib.lib()
+    cfg = dict(CFG)
+    if args.side:
+        cfg = cpu_sample_dims(CFG, args.side)
+    H, W, C, D = cfg["H"], cfg["W"], cfg["C"], cfg["D"]
+    sc = synth_scene(H, W, cfg["R"], C=C, P=cfg["P"], D=D, seed=cfg["seed"], device=dev)
+    R, N = sc.n_regions, sc.feats.shape[0]
+    eng = MergeEngine(H, W, R, D, C=C, n_points=N, device=dev)
+
+    def step():
+        return eng.run(sc.labels, sc.feats, cfg["tau"], image=sc.image, xs=sc.xs, ys=sc.ys)
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    torch.cuda.synchronize()
+    E0 = None
+
+    # ---- device-resident timing: exactly K steps in one bracket ------------------------------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = L.dm_launch_count()
+    with ClockSampler(local) as clocks:
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(args.steps):
+            res = step()
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = (L.dm_launch_count() - launches0)
+    mpx = H * W / ms / 1e3
+
+    # ---- the dominant kernel alone (fused RAG + band pooling raster pass), CUDA events -------------
+    s = _stream()
+    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for i in range(args.steps):
+        eng.stats.zero_()
+        k0[i].record()
+        L.check(L.dm_rag_scan(_p(sc.labels), H, H, W, W, _p(sc.image), C, W * C, R, 1, 1, _p(eng.area), _p(eng.border),
+                              _p(eng.bsum), _p(eng.bsq), eng.cap, _p(eng.counts), _p(eng.ws), eng.ws_bytes, s), "scan")
+        k1[i].record()
+    torch.cuda.synchronize()
+    rag_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)]))
+    rag = eng.run(sc.labels, sc.feats, cfg["tau"], image=sc.image, xs=sc.xs, ys=sc.ys, max_rounds=0)
+    E0 = int(rag.edge_keys.shape[0])
+    alg_bytes = (4 + C) * H * W + 12 * E0 + 16 * R * C
+    peak, peak_kind = measured_peaks()
+    achieved = alg_bytes / (rag_ms * 1e-3) / 1e9
+    res = step()
+
+    # ---- end to end through the public API with HOST buffers -----------------------------------------
+    from deepmerge_b200 import merge_scene
+    host = {k: getattr(sc, k).cpu().pin_memory() for k in ("labels", "image", "feats", "xs", "ys")}
+    out_host = torch.empty((H, W), dtype=torch.int32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+    d2h = out_host.numel() * 4
+
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        r = eng.run(d["labels"], d["feats"], cfg["tau"], image=d["image"], xs=d["xs"], ys=d["ys"])
+        out_host.copy_(r.labels, non_blocking=True)
+        torch.cuda.synchronize()
+        return r
+
+    e2e_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+
+    # ---- CPU baseline: the oracle port on a bounded sample, same box -----------------------------------
+    cpu = None
+    if not args.no_cpu:
+        ccfg = cpu_sample_dims(cfg, min(args.cpu_side, H))
+        sec, cres, csc = run_cpu_port(ccfg)
+        cpu = {"value": ccfg["H"] * ccfg["W"] / sec / 1e6, "unit": "Mpx/s", "cores": 1, "kind": "port",
+               "sample": f"{ccfg['H']}x{ccfg['W']} scene at the workload's region pitch ({csc['n_regions']} segments), "
+                         f"{ccfg['C']} bands; numpy oracle, single thread"}
+
+    n_roots = int((res.root == torch.arange(R, device=dev, dtype=torch.int32)).sum())
+    line = {
+        "metric": "megapixels/sec end-to-end (RAG+pool+score+merge+relabel)", "value": mpx, "unit": "Mpx/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32/u8 index + fp32 scores", "data": "synthetic",
+        "config": {"workload": WORKLOAD if not args.side else f"{H}x{W} reduced scene", "H": H, "W": W, "bands": C,
+                   "segments": R, "edges": E0, "points": N, "embed_dim": D, "tau": cfg["tau"],
+                   "l2_policy": "inputs (labels+image 800 MB) larger than L2, no flush needed"},
+        "merged_edges_per_s": res.merges / (ms * 1e-3), "scored_edges_per_s": E0 / (ms * 1e-3),
+        "segments_after": n_roots, "rounds": res.rounds,
+        "e2e": {"value": H * W / e2e_ms / 1e3, "unit": "Mpx/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "rag_pool_kernel (fused RAG + band pooling raster pass)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                     "frac_of_nominal_8TBs": achieved / 8000.0, "ms": rag_ms, "algorithmic_bytes": alg_bytes,
+                     "traffic": None},
+        "cpu_baseline": cpu, "clocks": clocks.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--side", type=int, default=0, help="debug: run a reduced side x side scene instead of configs[1]")
+    ap.add_argument("--cpu-side", type=int, default=2000, help="side of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,399 @@
+// R9: merge loop building blocks -- selection, lock-free union-find with minimum-id roots,
+// merged statistics with a deterministic fp32 summation order, edge re-keying, and the
+// final LUT relabel of the raster.  Spec: SURVEY.md section 8(a) R9 (the reference only
+// scores edges, ExtractFeatures.py:150-225, and never merges).
+#include "common.cuh"
+#include "prims.cuh"
+
+namespace dm {
+namespace merge {
+
+static unsigned grid_for(int64_t items, int threads = 256, int per_sm = 8) {
+    int64_t g = ceil_div(items, threads);
+    int64_t cap = (int64_t)num_sms() * per_sm;
+    return (unsigned)imax64(1, min(g, cap));
+}
+
+// ---- selection ------------------------------------------------------------------------
+template <bool MLP>
+__global__ void select_kernel(const float* __restrict__ v, float tau, int n_out, const int64_t* __restrict__ n_dev,
+                              uint8_t* __restrict__ selected, unsigned long long* __restrict__ n_sel) {
+    const int64_t n = *n_dev;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t start = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t e0 = start - threadIdx.x % 32; e0 < n; e0 += stride) {
+        const int64_t e = e0 + threadIdx.x % 32;
+        bool sel = false;
+        if (e < n) {
+            if (MLP) sel = v[e * n_out + 1] > v[e * n_out];   // argmax == 1 (ties go to class 0)
+            else sel = v[e] < tau;
+            selected[e] = sel ? 1 : 0;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, sel);
+        if (bal && (threadIdx.x & 31) == 0) atomicAdd(n_sel, (unsigned long long)__popc(bal));
+    }
+}
+
+// ---- union-find ---------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(const int32_t* parent, int x) {
+    int p = ((const volatile int32_t*)parent)[x];
+    while (p != x) {
+        x = p;
+        p = ((const volatile int32_t*)parent)[x];
+    }
+    return x;
+}
+
+// Hook the larger root under the smaller with atomicCAS and retry on contention: parent[x] <= x
+// always holds, so there are no cycles and every tree's root is its component's minimum id.
+__global__ void uf_union_kernel(int32_t* __restrict__ parent, const uint64_t* __restrict__ keys,
+                                const uint8_t* __restrict__ selected, const int64_t* __restrict__ n_dev) {
+    const int64_t n = *n_dev;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        if (!selected[e]) continue;
+        const uint64_t k = keys[e];
+        int a = uf_find(parent, key_lo(k));
+        int b = uf_find(parent, key_hi(k));
+        while (a != b) {
+            if (a > b) { int t = a; a = b; b = t; }          // a < b: hook b under a
+            const int old = atomicCAS(&parent[b], b, a);
+            if (old == b) break;
+            b = uf_find(parent, old);                         // b got hooked elsewhere meanwhile
+            a = uf_find(parent, a);
+        }
+    }
+}
+
+__global__ void uf_compress_kernel(int32_t* __restrict__ parent, int64_t n) {
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (int64_t)gridDim.x * blockDim.x) {
+        // roots never change here, so racing writes of final roots are benign
+        parent[x] = uf_find(parent, (int)x);
+    }
+}
+
+// ---- merged statistics ------------------------------------------------------------------------
+__global__ void collect_members_kernel(const int32_t* __restrict__ parent, uint8_t* __restrict__ alive,
+                                       uint8_t* __restrict__ changed, int32_t* __restrict__ cnt,
+                                       unsigned long long* __restrict__ area, unsigned long long* __restrict__ perimeter,
+                                       int64_t R, uint64_t* __restrict__ list, unsigned long long* __restrict__ n_list) {
+    for (int64_t x0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - (threadIdx.x & 31); x0 < R;
+         x0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t x = x0 + (threadIdx.x & 31);
+        bool moved = false;
+        int r = 0;
+        if (x < R && alive[x]) {
+            r = parent[x];
+            moved = r != (int)x;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, moved);
+        if (!bal) continue;
+        unsigned long long base = 0;
+        if ((threadIdx.x & 31) == 0) base = atomicAdd(n_list, (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (moved) {
+            alive[x] = 0;
+            changed[r] = 1;
+            atomicAdd(&cnt[r], cnt[x]);
+            atomicAdd(&area[r], area[x]);
+            atomicAdd(&perimeter[r], perimeter[x]);
+            list[base + __popc(bal & lanemask_lt())] = ((uint64_t)(unsigned)r << 32) | (unsigned)x;
+        }
+    }
+}
+
+// list sorted by (root, member).  The warp that lands on the head of a root's run adds the
+// members' sums into the root's sum one after another (ascending member id): a fixed fp32
+// summation order, so results do not depend on scheduling.
+__global__ void __launch_bounds__(256) merge_sums_kernel(const uint64_t* __restrict__ list,
+                                                         const int64_t* __restrict__ n_dev, float* __restrict__ sum,
+                                                         int D) {
+    const int64_t n = *n_dev;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarps) {
+        const int root = key_lo(list[i]);
+        if (i > 0 && key_lo(list[i - 1]) == root) continue;
+        for (int d = lane; d < D; d += 32) {
+            float acc = sum[(int64_t)root * D + d];
+            for (int64_t j = i; j < n && key_lo(list[j]) == root; ++j) acc += sum[(int64_t)key_hi(list[j]) * D + d];
+            sum[(int64_t)root * D + d] = acc;
+        }
+    }
+}
+
+// ---- edge re-keying -----------------------------------------------------------------------------
+__global__ void rekey_kernel(const int32_t* __restrict__ parent, const uint64_t* __restrict__ keys,
+                             const uint32_t* __restrict__ lens, const int64_t* __restrict__ n_dev, uint64_t sentinel,
+                             unsigned long long* __restrict__ perimeter, uint64_t* __restrict__ new_keys,
+                             uint32_t* __restrict__ perm) {
+    const int64_t n = *n_dev;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[e];
+        const int a = parent[key_lo(k)], b = parent[key_hi(k)];
+        perm[e] = (uint32_t)e;
+        if (a == b) {   // the boundary became internal: both of its sides leave the perimeter
+            atomicAdd(&perimeter[a], (unsigned long long)(-2ll * (long long)lens[e]));
+            new_keys[e] = sentinel;
+        } else {
+            new_keys[e] = pack_key(a, b);
+        }
+    }
+}
+
+__global__ void copy_edges_kernel(const uint64_t* __restrict__ k, const uint32_t* __restrict__ l, const float* __restrict__ s,
+                                  const int64_t* __restrict__ n_dev, uint64_t* __restrict__ ko, uint32_t* __restrict__ lo,
+                                  float* __restrict__ so) {
+    const int64_t n = *n_dev;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        ko[e] = k[e];
+        lo[e] = l[e];
+        if (s) so[e] = s[e];
+    }
+}
+
+// ---- relabel ------------------------------------------------------------------------------------
+__device__ __forceinline__ int lut(const int32_t* __restrict__ root, int l, int R) {
+    return (unsigned)l < (unsigned)R ? __ldg(root + l) : l;
+}
+
+// 128-bit streaming loads/stores; the root LUT (4 B x R) stays in L2 / L1.
+__global__ void __launch_bounds__(256) relabel_vec_kernel(const int4* __restrict__ in, int64_t n4,
+                                                          const int32_t* __restrict__ root, int R, int4* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {   // 4 independent 16-byte loads in flight per thread
+        int4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg_stream(in + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u].x = lut(root, v[u].x, R);
+            v[u].y = lut(root, v[u].y, R);
+            v[u].z = lut(root, v[u].z, R);
+            v[u].w = lut(root, v[u].w, R);
+            stg_stream(out + i + u * stride, v[u]);
+        }
+    }
+    for (; i < n4; i += stride) {
+        int4 v = ldg_stream(in + i);
+        v.x = lut(root, v.x, R);
+        v.y = lut(root, v.y, R);
+        v.z = lut(root, v.z, R);
+        v.w = lut(root, v.w, R);
+        stg_stream(out + i, v);
+    }
+}
+
+__global__ void relabel_scalar_kernel(const int32_t* __restrict__ in, int64_t H, int64_t W, int64_t ld_in,
+                                      const int32_t* __restrict__ root, int R, int32_t* __restrict__ out, int64_t ld_out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t y = i / W, x = i - y * W;
+        out[y * ld_out + x] = lut(root, in[y * ld_in + x], R);
+    }
+}
+
+__global__ void root_flags_kernel(const int32_t* __restrict__ root, int64_t R, uint32_t* __restrict__ flags,
+                                  int64_t* __restrict__ n_dev) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_dev = R;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < R; x += (int64_t)gridDim.x * blockDim.x)
+        flags[x] = root[x] == (int)x ? 1u : 0u;
+}
+__global__ void compact_kernel(const int32_t* __restrict__ root, int64_t R, const uint32_t* __restrict__ excl,
+                               int32_t* __restrict__ compact) {
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < R; x += (int64_t)gridDim.x * blockDim.x) {
+        const int r = root[x];
+        compact[x] = (unsigned)r < (unsigned)R ? (int)excl[r] : -1;
+    }
+}
+
+__global__ void perimeter_init_kernel(const int64_t* __restrict__ border, int64_t* __restrict__ perimeter, int64_t R) {
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < R; x += (int64_t)gridDim.x * blockDim.x)
+        perimeter[x] = border[x];
+}
+__global__ void perimeter_edges_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ lens,
+                                       const int64_t* __restrict__ n_dev, unsigned long long* __restrict__ perimeter,
+                                       int64_t R) {
+    const int64_t n = *n_dev;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[e];
+        if (key_hi(k) >= R) continue;
+        atomicAdd(&perimeter[key_lo(k)], (unsigned long long)lens[e]);
+        atomicAdd(&perimeter[key_hi(k)], (unsigned long long)lens[e]);
+    }
+}
+
+}  // namespace merge
+}  // namespace dm
+
+using namespace dm;
+using merge::grid_for;
+
+extern "C" int dm_merge_select_l2(const float* scores, float tau, const int64_t* n_dev, int64_t capacity, uint8_t* selected,
+                                  int64_t* n_sel, dm_stream_t stream) {
+    if (capacity < 0 || !n_sel) return DM_ERR_BAD_ARG;
+    DM_CUDA(cudaMemsetAsync(n_sel, 0, sizeof(int64_t), S(stream)));
+    if (capacity == 0) return DM_OK;
+    if (!scores || !n_dev || !selected) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::select_kernel<false><<<grid_for(capacity), 256, 0, S(stream)>>>(scores, tau, 1, n_dev, selected,
+                                                                           (unsigned long long*)n_sel);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_merge_select_mlp(const float* o, int64_t n_out, const int64_t* n_dev, int64_t capacity, uint8_t* selected,
+                                   int64_t* n_sel, dm_stream_t stream) {
+    if (capacity < 0 || !n_sel || n_out < 2) return DM_ERR_BAD_ARG;
+    DM_CUDA(cudaMemsetAsync(n_sel, 0, sizeof(int64_t), S(stream)));
+    if (capacity == 0) return DM_OK;
+    if (!o || !n_dev || !selected) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::select_kernel<true><<<grid_for(capacity), 256, 0, S(stream)>>>(o, 0.f, (int)n_out, n_dev, selected,
+                                                                          (unsigned long long*)n_sel);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_uf_union(int32_t* parent, const uint64_t* keys, const uint8_t* selected, const int64_t* n_dev,
+                           int64_t capacity, dm_stream_t stream) {
+    if (capacity < 0) return DM_ERR_BAD_ARG;
+    if (capacity == 0) return DM_OK;
+    if (!parent || !keys || !selected || !n_dev) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::uf_union_kernel<<<grid_for(capacity), 256, 0, S(stream)>>>(parent, keys, selected, n_dev);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_uf_compress(int32_t* parent, int64_t R, dm_stream_t stream) {
+    if (R < 0) return DM_ERR_BAD_ARG;
+    if (R == 0) return DM_OK;
+    if (!parent) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::uf_compress_kernel<<<grid_for(R), 256, 0, S(stream)>>>(parent, R);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" size_t dm_merge_apply_workspace_bytes(int64_t R) {
+    const int64_t cap = R < 1 ? 1 : R;
+    return align_up((size_t)cap * 8, 256) + prims::sort_ws_bytes(cap) + 256;
+}
+
+extern "C" int dm_merge_apply(const int32_t* parent, uint8_t* alive, uint8_t* changed, float* sum, int32_t* cnt,
+                              int64_t* area, int64_t* perimeter, int64_t R, int64_t D, int64_t* n_merged, void* ws,
+                              size_t ws_bytes, dm_stream_t stream) {
+    if (R < 0 || D <= 0 || !n_merged) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    DM_CUDA(cudaMemsetAsync(n_merged, 0, sizeof(int64_t), s));
+    if (R == 0) return DM_OK;
+    if (!parent || !alive || !changed || !sum || !cnt || !area || !perimeter || !ws) return DM_ERR_BAD_ARG;
+    if (ws_bytes < dm_merge_apply_workspace_bytes(R)) return DM_ERR_WORKSPACE;
+    Carver c(ws);
+    uint64_t* list = c.take<uint64_t>(R);
+    void* sws = c.take<char>(prims::sort_ws_bytes(R));
+    DM_CUDA(cudaMemsetAsync(changed, 0, (size_t)R, s));
+    DM_COUNT_LAUNCH(); merge::collect_members_kernel<<<grid_for(R), 256, 0, s>>>(parent, alive, changed, cnt, (unsigned long long*)area,
+                                                              (unsigned long long*)perimeter, R, list,
+                                                              (unsigned long long*)n_merged);
+    const int b = bits_for(R);
+    DM_TRY(prims::sort_pairs(list, nullptr, n_merged, R, b, 2 * b, sws, s));
+    DM_COUNT_LAUNCH(); merge::merge_sums_kernel<<<grid_for(R * 32), 256, 0, s>>>(list, n_merged, sum, (int)D);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" size_t dm_edges_rekey_workspace_bytes(int64_t capacity) {
+    const int64_t cap = capacity < 1 ? 1 : capacity;
+    return 2 * align_up((size_t)cap * 8, 256) + 3 * align_up((size_t)cap * 4, 256) + prims::sort_ws_bytes(cap) +
+           prims::unique_ws_bytes(cap) + 256;
+}
+
+extern "C" int dm_edges_rekey(const int32_t* parent, uint64_t* keys, uint32_t* lens, float* scores, int64_t* n_dev,
+                              int64_t capacity, int64_t R, int64_t* perimeter, void* ws, size_t ws_bytes,
+                              dm_stream_t stream) {
+    if (capacity < 0 || R < 0) return DM_ERR_BAD_ARG;
+    if (capacity == 0) return DM_OK;
+    if (!parent || !keys || !lens || !n_dev || !perimeter || !ws) return DM_ERR_BAD_ARG;
+    if (ws_bytes < dm_edges_rekey_workspace_bytes(capacity)) return DM_ERR_WORKSPACE;
+    cudaStream_t s = S(stream);
+    Carver c(ws);
+    uint64_t* nk = c.take<uint64_t>(capacity);
+    uint64_t* ok = c.take<uint64_t>(capacity);
+    uint32_t* perm = c.take<uint32_t>(capacity);
+    uint32_t* ol = c.take<uint32_t>(capacity);
+    float* os = c.take<float>(capacity);
+    void* sws = c.take<char>(prims::sort_ws_bytes(capacity));
+    void* uws = c.take<char>(prims::unique_ws_bytes(capacity));
+    const uint64_t sentinel = ((uint64_t)R << 32) | (uint64_t)R;
+    DM_COUNT_LAUNCH(); merge::rekey_kernel<<<grid_for(capacity), 256, 0, s>>>(parent, keys, lens, n_dev, sentinel,
+                                                           (unsigned long long*)perimeter, nk, perm);
+    const int b = bits_for(R + 1);
+    DM_TRY(prims::sort_pairs(nk, perm, n_dev, capacity, b, 2 * b, sws, s));
+    int64_t* n_new = c.take<int64_t>(1);
+    DM_TRY(prims::unique_reduce(nk, perm, lens, scores, n_dev, capacity, sentinel, ok, ol, scores ? os : nullptr, n_new,
+                                uws, s));
+    DM_COUNT_LAUNCH(); merge::copy_edges_kernel<<<grid_for(capacity), 256, 0, s>>>(ok, ol, scores ? os : nullptr, n_new, keys, lens, scores);
+    DM_CUDA(cudaMemcpyAsync(n_dev, n_new, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_relabel(const int32_t* labels, int64_t H, int64_t W, int64_t ld_in, const int32_t* root, int64_t R,
+                          int32_t* out, int64_t ld_out, dm_stream_t stream) {
+    if (H < 0 || W < 0 || ld_in < W || ld_out < W || R < 0 || R > 0x7fffffff) return DM_ERR_BAD_ARG;
+    if (H == 0 || W == 0) return DM_OK;
+    if (!labels || !out || (!root && R > 0)) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    const bool dense = (ld_in == W && ld_out == W);
+    const int64_t n = H * W;
+    if (dense && n % 4 == 0 && (uintptr_t)labels % 16 == 0 && (uintptr_t)out % 16 == 0) {
+        const int64_t n4 = n / 4;
+        // 4 x 16 B per thread per trip; grid sized to a whole number of waves of the SM count
+        const unsigned g = (unsigned)imax64(1, imin64(ceil_div(n4, 256 * 4), (int64_t)num_sms() * 8));
+        DM_COUNT_LAUNCH(); merge::relabel_vec_kernel<<<g, 256, 0, s>>>((const int4*)labels, n4, root, (int)R, (int4*)out);
+    } else {
+        DM_COUNT_LAUNCH(); merge::relabel_scalar_kernel<<<grid_for(n), 256, 0, s>>>(labels, H, W, ld_in, root, (int)R, out, ld_out);
+    }
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" size_t dm_compact_roots_workspace_bytes(int64_t R) {
+    const int64_t cap = R < 1 ? 1 : R;
+    return 2 * align_up((size_t)cap * 4, 256) + prims::scan_ws_bytes(cap) + 256;
+}
+
+extern "C" int dm_compact_roots(const int32_t* root, int64_t R, int32_t* compact, int64_t* n_roots, void* ws,
+                                size_t ws_bytes, dm_stream_t stream) {
+    if (R < 0 || !n_roots) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    if (R == 0) {
+        DM_CUDA(cudaMemsetAsync(n_roots, 0, sizeof(int64_t), s));
+        return DM_OK;
+    }
+    if (!root || !compact || !ws) return DM_ERR_BAD_ARG;
+    if (ws_bytes < dm_compact_roots_workspace_bytes(R)) return DM_ERR_WORKSPACE;
+    Carver c(ws);
+    uint32_t* flags = c.take<uint32_t>(R);
+    uint32_t* excl = c.take<uint32_t>(R);
+    void* sws = c.take<char>(prims::scan_ws_bytes(R));
+    int64_t* n_dev = c.take<int64_t>(1);
+    DM_COUNT_LAUNCH(); merge::root_flags_kernel<<<grid_for(R), 256, 0, s>>>(root, R, flags, n_dev);
+    DM_TRY(prims::scan_exclusive_u32(flags, excl, n_dev, R, n_roots, sws, s));
+    DM_COUNT_LAUNCH(); merge::compact_kernel<<<grid_for(R), 256, 0, s>>>(root, R, excl, compact);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_perimeter(const uint64_t* keys, const uint32_t* lens, const int64_t* n_dev, int64_t capacity,
+                            const int64_t* border, int64_t* perimeter, int64_t R, dm_stream_t stream) {
+    if (capacity < 0 || R < 0) return DM_ERR_BAD_ARG;
+    if (R == 0) return DM_OK;
+    if (!border || !perimeter) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    DM_COUNT_LAUNCH(); merge::perimeter_init_kernel<<<grid_for(R), 256, 0, s>>>(border, perimeter, R);
+    if (capacity > 0) {
+        if (!keys || !lens || !n_dev) return DM_ERR_BAD_ARG;
+        DM_COUNT_LAUNCH(); merge::perimeter_edges_kernel<<<grid_for(capacity), 256, 0, s>>>(keys, lens, n_dev, (unsigned long long*)perimeter, R);
+    }
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}

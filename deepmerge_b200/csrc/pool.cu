@@ -1,0 +1,276 @@
+// R3-R5: region -> sample-point membership and mean pooling; per-pixel embedding pooling.
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "prims.cuh"
+
+namespace dm {
+namespace pool {
+
+__global__ void points_region_kernel(const int32_t* __restrict__ labels, int64_t H, int64_t W, int64_t ld,
+                                     const int32_t* __restrict__ xs, const int32_t* __restrict__ ys, int64_t n,
+                                     int32_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = xs[i], y = ys[i];
+        int l = -1;
+        if (x >= 0 && x < W && y >= 0 && y < H) l = labels[(int64_t)y * ld + x];
+        out[i] = l < 0 ? -1 : l;
+    }
+}
+
+// key = region (invalid -> n_regions, sorts last), value = point id
+__global__ void csr_keys_kernel(const int32_t* __restrict__ rop, int64_t n, int64_t n_regions, uint64_t* __restrict__ keys,
+                                uint32_t* __restrict__ vals, int64_t* __restrict__ n_dev) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_dev = n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = rop[i];
+        keys[i] = (r >= 0 && r < n_regions) ? (uint64_t)r : (uint64_t)n_regions;
+        vals[i] = (uint32_t)i;
+    }
+}
+
+// offsets[r] = first sorted position whose key >= r, for r in [0, R]
+__global__ void csr_offsets_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n,
+                                   int64_t n_regions, int64_t* __restrict__ offsets, int32_t* __restrict__ point_ids) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t cur = i < n ? (int64_t)keys[i] : n_regions + 1;       // virtual terminator
+        const int64_t prev = i > 0 ? (int64_t)keys[i - 1] : -1;
+        const int64_t hi = cur < n_regions ? cur : n_regions;
+        for (int64_t r = prev + 1; r <= hi; ++r) offsets[r] = i;
+        if (i < n && cur < n_regions) point_ids[i] = (int32_t)vals[i];
+    }
+}
+
+// One warp per region, lanes over the feature dimension, points visited in membership
+// order: sum = ((f0 + f1) + f2) + ...  exactly like np.mean's row-by-row reduction
+// (ExtractFeatures.py:211-212).  K*32 feature columns per pass starting at d_base.
+template <int K>
+__global__ void __launch_bounds__(256) pool_points_kernel(const int64_t* __restrict__ offsets,
+                                                          const int32_t* __restrict__ ids, const float* __restrict__ feats,
+                                                          int64_t ld, int64_t R, int D, int d_base, float* __restrict__ sum,
+                                                          int32_t* __restrict__ cnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < R; r += nwarps) {
+        const int64_t a = offsets[r], b = offsets[r + 1];
+        float acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.f;
+        int64_t j = a;
+        for (; j + 4 <= b; j += 4) {   // 4 rows of loads in flight; the adds stay in order
+            float v[4][K];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float* row = feats + (int64_t)ids[j + u] * ld + d_base;
+#pragma unroll
+                for (int k = 0; k < K; ++k) v[u][k] = (d_base + lane + 32 * k < D) ? row[lane + 32 * k] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] += v[u][k];
+        }
+        for (; j < b; ++j) {
+            const float* row = feats + (int64_t)ids[j] * ld + d_base;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (d_base + lane + 32 * k < D) acc[k] += row[lane + 32 * k];
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (d_base + lane + 32 * k < D) sum[r * D + d_base + lane + 32 * k] = acc[k];
+        if (lane == 0 && d_base == 0) cnt[r] = (int32_t)(b - a);
+    }
+}
+
+// mean = sum / max(cnt,1) with an IEEE fp32 division (np.mean divides the fp32 sum by n),
+// norm2 = sum_d mean^2 reduced in a fixed lane/shuffle order (deterministic).
+__global__ void __launch_bounds__(256) region_mean_kernel(const float* __restrict__ sum, const int32_t* __restrict__ cnt,
+                                                          int64_t R, int D, float* __restrict__ mean,
+                                                          float* __restrict__ norm2, const uint8_t* __restrict__ only) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < R; r += nwarps) {
+        if (only && !only[r]) continue;
+        const float c = (float)max(cnt[r], 1);
+        float n2 = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float m = __fdiv_rn(sum[r * D + d], c);
+            mean[r * D + d] = m;
+            n2 = __fmaf_rn(m, m, n2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        if (lane == 0) norm2[r] = n2;
+    }
+}
+
+// Per-pixel embedding pooling.  A warp walks a run of pixels of one raster row; lanes hold
+// 32-column slices of the current label's partial sum in registers and flush it with one
+// fp32 atomic per column only when the label changes (run-length pre-aggregation).
+template <typename T, int K>
+__global__ void __launch_bounds__(256) pool_dense_kernel(const int32_t* __restrict__ labels, int64_t H, int64_t W,
+                                                         int64_t ld, const T* __restrict__ emb, int D, int d_base,
+                                                         int64_t n_regions, float* __restrict__ sum,
+                                                         int32_t* __restrict__ cnt, int chunk) {
+    const int lane = threadIdx.x & 31;
+    const int64_t chunks_per_row = (W + chunk - 1) / chunk;
+    const int64_t total = H * chunks_per_row;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = warp0; w < total; w += nwarps) {
+        const int64_t y = w / chunks_per_row;
+        const int64_t xa = (w - y * chunks_per_row) * chunk;
+        const int64_t xb = min(W, xa + chunk);
+        float acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.f;
+        int cur = -1, run = 0;
+        for (int64_t x = xa; x < xb; ++x) {
+            int l = labels[y * ld + x];
+            if (l >= n_regions) l = -1;
+            if (l != cur) {
+                if (cur >= 0) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        if (d_base + lane + 32 * k < D) atomicAdd(&sum[(int64_t)cur * D + d_base + lane + 32 * k], acc[k]);
+                    if (lane == 0 && d_base == 0) atomicAdd(&cnt[cur], run);
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = 0.f;
+                cur = l;
+                run = 0;
+            }
+            if (l >= 0) {
+                const T* e = emb + (y * W + x) * (int64_t)D + d_base;
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (d_base + lane + 32 * k < D) acc[k] += (float)e[lane + 32 * k];
+                ++run;
+            }
+        }
+        if (cur >= 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (d_base + lane + 32 * k < D) atomicAdd(&sum[(int64_t)cur * D + d_base + lane + 32 * k], acc[k]);
+            if (lane == 0 && d_base == 0) atomicAdd(&cnt[cur], run);
+        }
+    }
+}
+
+static unsigned grid_for(int64_t work_items, int threads, int per_sm) {
+    int64_t g = ceil_div(work_items, threads);
+    int64_t cap = (int64_t)num_sms() * per_sm;
+    return (unsigned)imax64(1, min(g, cap));
+}
+
+}  // namespace pool
+}  // namespace dm
+
+using namespace dm;
+
+extern "C" int dm_points_region(const int32_t* labels, int64_t H, int64_t W, int64_t ld, const int32_t* xs,
+                                const int32_t* ys, int64_t n, int32_t* out, dm_stream_t stream) {
+    if (n < 0 || H < 0 || W < 0 || ld < W) return DM_ERR_BAD_ARG;
+    if (n == 0) return DM_OK;
+    if (!labels || !xs || !ys || !out) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); pool::points_region_kernel<<<pool::grid_for(n, 256, 8), 256, 0, S(stream)>>>(labels, H, W, ld, xs, ys, n, out);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" size_t dm_csr_workspace_bytes(int64_t n_points, int64_t n_regions) {
+    (void)n_regions;
+    const int64_t cap = n_points < 1 ? 1 : n_points;
+    return align_up((size_t)cap * 8, 256) + align_up((size_t)cap * 4, 256) + 256 + prims::sort_ws_bytes(cap);
+}
+
+extern "C" int dm_csr_build(const int32_t* rop, int64_t n, int64_t R, int64_t* offsets, int32_t* point_ids, void* ws,
+                            size_t ws_bytes, dm_stream_t stream) {
+    if (n < 0 || R < 0 || !offsets) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    if (n == 0) {
+        DM_CUDA(cudaMemsetAsync(offsets, 0, (size_t)(R + 1) * sizeof(int64_t), s));
+        return DM_OK;
+    }
+    if (!rop || !point_ids || !ws) return DM_ERR_BAD_ARG;
+    if (ws_bytes < dm_csr_workspace_bytes(n, R)) return DM_ERR_WORKSPACE;
+    Carver c(ws);
+    uint64_t* keys = c.take<uint64_t>(n);
+    uint32_t* vals = c.take<uint32_t>(n);
+    int64_t* n_dev = c.take<int64_t>(1);
+    void* sws = c.take<char>(prims::sort_ws_bytes(n));
+    const unsigned g = pool::grid_for(n, 256, 8);
+    DM_COUNT_LAUNCH(); pool::csr_keys_kernel<<<g, 256, 0, s>>>(rop, n, R, keys, vals, n_dev);
+    // stable sort by region only (input is in ascending point id): low bits_for(R+1) bits
+    const int b = bits_for(R + 1);
+    DM_TRY(prims::sort_pairs(keys, vals, n_dev, n, b, b, sws, s));
+    DM_COUNT_LAUNCH(); pool::csr_offsets_kernel<<<pool::grid_for(n + 1, 256, 8), 256, 0, s>>>(keys, vals, n, R, offsets, point_ids);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+template <int K>
+static void launch_pool_points(const int64_t* offsets, const int32_t* ids, const float* feats, int64_t ld, int64_t R,
+                               int D, int d_base, float* sum, int32_t* cnt, cudaStream_t s) {
+    DM_COUNT_LAUNCH(); pool::pool_points_kernel<K><<<pool::grid_for(R * 32, 256, 8), 256, 0, s>>>(offsets, ids, feats, ld, R, D, d_base, sum, cnt);
+}
+
+extern "C" int dm_pool_points_csr(const int64_t* offsets, const int32_t* ids, const float* feats, int64_t ld, int64_t R,
+                                  int64_t D, float* sum, int32_t* cnt, dm_stream_t stream) {
+    if (R < 0 || D <= 0 || ld < D || D > (1 << 20)) return DM_ERR_BAD_ARG;
+    if (R == 0) return DM_OK;
+    if (!offsets || !sum || !cnt) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    for (int d0 = 0; d0 < D; d0 += 128) {
+        const int rem = (int)D - d0;
+        if (rem > 96) launch_pool_points<4>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, s);
+        else if (rem > 64) launch_pool_points<3>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, s);
+        else if (rem > 32) launch_pool_points<2>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, s);
+        else launch_pool_points<1>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, s);
+    }
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_region_mean(const float* sum, const int32_t* cnt, int64_t R, int64_t D, float* mean, float* norm2,
+                              const uint8_t* only, dm_stream_t stream) {
+    if (R < 0 || D <= 0) return DM_ERR_BAD_ARG;
+    if (R == 0) return DM_OK;
+    if (!sum || !cnt || !mean || !norm2) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); pool::region_mean_kernel<<<pool::grid_for(R * 32, 256, 8), 256, 0, S(stream)>>>(sum, cnt, R, (int)D, mean, norm2, only);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+template <typename T>
+static int pool_dense_t(const int32_t* labels, int64_t H, int64_t W, int64_t ld, const T* emb, int64_t D, int64_t R,
+                        float* sum, int32_t* cnt, cudaStream_t s) {
+    const int chunk = 64;
+    const int64_t warps = H * ceil_div(W, chunk);
+    const unsigned g = pool::grid_for(warps * 32, 256, 8);
+    for (int d0 = 0; d0 < D; d0 += 128) {
+        const int rem = (int)D - d0;
+        if (rem > 96) {
+            DM_COUNT_LAUNCH(); pool::pool_dense_kernel<T, 4><<<g, 256, 0, s>>>(labels, H, W, ld, emb, (int)D, d0, R, sum, cnt, chunk);
+        } else if (rem > 64) {
+            DM_COUNT_LAUNCH(); pool::pool_dense_kernel<T, 3><<<g, 256, 0, s>>>(labels, H, W, ld, emb, (int)D, d0, R, sum, cnt, chunk);
+        } else if (rem > 32) {
+            DM_COUNT_LAUNCH(); pool::pool_dense_kernel<T, 2><<<g, 256, 0, s>>>(labels, H, W, ld, emb, (int)D, d0, R, sum, cnt, chunk);
+        } else {
+            DM_COUNT_LAUNCH(); pool::pool_dense_kernel<T, 1><<<g, 256, 0, s>>>(labels, H, W, ld, emb, (int)D, d0, R, sum, cnt, chunk);
+        }
+    }
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_dense(const int32_t* labels, int64_t H, int64_t W, int64_t ld, const void* emb, int dtype_bf16,
+                             int64_t D, int64_t R, float* sum, int32_t* cnt, dm_stream_t stream) {
+    if (H < 0 || W < 0 || ld < W || D <= 0 || R < 0) return DM_ERR_BAD_ARG;
+    if (H == 0 || W == 0) return DM_OK;
+    if (!labels || !emb || !sum || !cnt) return DM_ERR_BAD_ARG;
+    if (dtype_bf16) return pool_dense_t<__nv_bfloat16>(labels, H, W, ld, (const __nv_bfloat16*)emb, D, R, sum, cnt, S(stream));
+    return pool_dense_t<float>(labels, H, W, ld, (const float*)emb, D, R, sum, cnt, S(stream));
+}

@@ -1,0 +1,70 @@
+// Device-wide primitives used by the graph stages: exclusive scan, stable LSD radix
+// sort of packed edge keys, and sorted-run reduction (unique + sum).  All take their
+// element count from device memory so that stages chain without host round trips.
+#pragma once
+#include "common.cuh"
+
+namespace dm {
+namespace prims {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+
+size_t scan_ws_bytes(int64_t cap);
+int scan_exclusive_u32(const uint32_t* in, uint32_t* out, const int64_t* n_dev, int64_t cap,
+                       int64_t* total_dev, void* ws, cudaStream_t s);
+
+size_t sort_ws_bytes(int64_t cap);
+// Stable sort of (keys, vals) in place by the low key_bits bits of the compacted key
+// ((hi32 << id_bits) | lo32); both 32-bit halves of every key must be < 2^id_bits.
+// key_bits = 2*id_bits sorts by (hi, lo); key_bits = id_bits sorts by lo only.  vals may be null.
+int sort_pairs(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t cap, int id_bits, int key_bits,
+               void* ws, cudaStream_t s);
+
+size_t unique_ws_bytes(int64_t cap);
+// keys sorted.  For every run of equal keys (runs of `sentinel` are dropped):
+//   out_keys[r] = key, out_lens[r] = sum lens_in[perm ? perm[i] : i],
+//   out_scores[r] = scores_in[perm ? perm[i] : i] of the run head (when scores_in != null).
+int unique_reduce(const uint64_t* keys, const uint32_t* perm, const uint32_t* lens_in, const float* scores_in,
+                  const int64_t* n_dev, int64_t cap, uint64_t sentinel, uint64_t* out_keys, uint32_t* out_lens,
+                  float* out_scores, int64_t* n_out_dev, void* ws, cudaStream_t s);
+
+// ---- device helpers -------------------------------------------------------------------
+
+// Block-wide exclusive scan of one uint32 per thread.  smem needs NT/32 + 1 words.
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* smem, uint32_t& total) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < NT / 32 ? smem[lane] : 0;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (unsigned)o) winc += t;
+        }
+        if (lane < NT / 32) smem[lane] = winc - w;
+        if (lane == 31) smem[NT / 32] = winc;
+    }
+    __syncthreads();
+    uint32_t r = smem[warp] + inc - v;
+    total = smem[NT / 32];
+    __syncthreads();
+    return r;
+}
+
+}  // namespace prims
+}  // namespace dm

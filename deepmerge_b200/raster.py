@@ -1,0 +1,496 @@
+"""Raster-native entry points of the region-merging hot path.
+
+Thin PyTorch host code over the C ABI (include/deepmerge_b200.h): torch only owns device
+memory and streams; every computation is a hand-written sm_100a kernel in
+libdeepmerge_b200.so.  No CPU / eager fallback exists: tensors must live on a CUDA device.
+
+Edge keys are returned as int64 tensors holding (min << 32) | max (ids < 2^31, so the
+signed view orders like the unsigned key).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from ._lib import lib
+
+_I64, _I32, _U8, _F32 = torch.int64, torch.int32, torch.uint8, torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ValueError("deepmerge_b200 kernels need CUDA tensors (there is no CPU path)")
+
+
+def _labels_2d(labels):
+    if labels.dim() != 2 or labels.dtype != _I32:
+        raise ValueError("labels must be an int32 [H, W] tensor")
+    if labels.stride(1) != 1:
+        labels = labels.contiguous()
+    return labels
+
+
+@dataclass
+class RAG:
+    edge_keys: torch.Tensor       # int64 [E] sorted unique (min<<32)|max
+    boundary_len: torch.Tensor    # int32 [E] (uint32 counts)
+    area: torch.Tensor            # int64 [R]
+    perimeter: torch.Tensor       # int64 [R]
+    border: torch.Tensor          # int64 [R] sides facing the image border / nodata
+    band_sum: Optional[torch.Tensor] = None    # int64 [R, C] (uint64 values)
+    band_sumsq: Optional[torch.Tensor] = None  # int64 [R, C]
+
+    @property
+    def n_edges(self):
+        return self.edge_keys.shape[0]
+
+    def endpoints(self):
+        return self.edge_keys >> 32, self.edge_keys & 0xFFFFFFFF
+
+
+def default_edge_capacity(n_regions, H, W):
+    return int(max(1 << 16, min(2 * H * W, 8 * n_regions + 4 * (H + W))))
+
+
+def build_rag(labels: torch.Tensor, n_regions: int, image: Optional[torch.Tensor] = None, *, rows_own=None,
+              top_border=True, bottom_border=True, capacity=None, return_raw=False) -> RAG:
+    """RAG of a label raster, fused with band pooling when `image` (uint8 [H,W,C]) is given.
+
+    Replaces the edge list the reference reads from lines.shp (MyUtils2.py:155-193) and the
+    area / peri / mean / std polygon attributes (MyUtils1.py:79-114).  `rows_own` < H marks
+    the last row as a halo (row-tile sharding)."""
+    L = lib()
+    labels = _labels_2d(labels)
+    _need_cuda(labels, image)
+    H, W = labels.shape
+    own = H if rows_own is None else int(rows_own)
+    if own not in (H, H - 1):
+        raise ValueError("rows_own must be H or H-1 (one halo row)")
+    dev = labels.device
+    C = 0
+    if image is not None:
+        if image.dtype != _U8 or image.dim() != 3 or image.shape[0] < own or image.shape[1] != W:
+            raise ValueError("image must be uint8 [H, W, C]")
+        image = image.contiguous()
+        C = image.shape[2]
+    cap = default_edge_capacity(n_regions, H, W) if capacity is None else int(capacity)
+    with torch.cuda.device(dev):
+        while True:
+            area = torch.zeros(n_regions, dtype=_I64, device=dev)
+            border = torch.zeros(n_regions, dtype=_I64, device=dev)
+            bsum = torch.zeros((n_regions, C), dtype=_I64, device=dev) if C else None
+            bsq = torch.zeros((n_regions, C), dtype=_I64, device=dev) if C else None
+            keys = torch.empty(max(cap, 1), dtype=_I64, device=dev)
+            blen = torch.empty(max(cap, 1), dtype=_I32, device=dev)
+            counts = torch.zeros(4, dtype=_I64, device=dev)
+            ws_bytes = L.dm_rag_workspace_bytes(cap)
+            ws = torch.empty(ws_bytes, dtype=_U8, device=dev)
+            L.check(L.dm_rag_build(_p(labels), own, H, W, labels.stride(0), _p(image), C, W * C if C else 0, n_regions,
+                                   int(top_border), int(bottom_border), _p(area), _p(border), _p(bsum), _p(bsq),
+                                   _p(keys), _p(blen), cap, _p(counts), _p(ws), ws_bytes, _stream()), "dm_rag_build")
+            c = counts.tolist()
+            if c[3] == 1:
+                raise ValueError("labels contain ids >= n_regions")
+            if c[3] != 0:
+                raise RuntimeError("dm_rag_build: internal pipeline error")
+            if c[2] == 0:
+                break
+            cap = int(c[1]) + 1024          # overflow: counts[1] is the exact raw size needed
+        E = int(c[0])
+        perim = torch.empty(n_regions, dtype=_I64, device=dev)
+        L.check(L.dm_perimeter(_p(keys), _p(blen), _p(counts), cap, _p(border), _p(perim), n_regions, _stream()),
+                "dm_perimeter")
+    rag = RAG(keys[:E], blen[:E], area, perim, border, bsum, bsq)
+    if return_raw:
+        return rag, int(c[1])
+    return rag
+
+
+def pool_bands(labels, image, n_regions):
+    """Per-region band sums / sums of squares (uint64 exact) -> (sum, sumsq) int64 [R, C]."""
+    r = build_rag(labels, n_regions, image, capacity=None)
+    return r.band_sum, r.band_sumsq
+
+
+def merge_edge_lists(keys: torch.Tensor, lens: torch.Tensor, n_regions: int):
+    """Sort + unique (summing lengths) a concatenation of per-tile edge lists."""
+    L = lib()
+    _need_cuda(keys, lens)
+    n = keys.shape[0]
+    keys = keys.clone()
+    lens = lens.clone()
+    dev = keys.device
+    with torch.cuda.device(dev):
+        cnt = torch.tensor([n, 0], dtype=_I64, device=dev)
+        wsb = L.dm_edges_unique_workspace_bytes(n)
+        ws = torch.empty(wsb, dtype=_U8, device=dev)
+        L.check(L.dm_edges_sort_unique(_p(keys), _p(lens), _p(cnt), n, n_regions, cnt[1:].data_ptr(), _p(ws), wsb,
+                                       _stream()), "dm_edges_sort_unique")
+        E = int(cnt[1].item())
+    return keys[:E], lens[:E]
+
+
+def points_region(labels, xs, ys):
+    """region_of_point[i] = labels[ys[i], xs[i]] (-1 outside / nodata): the raster form of the
+    PointID membership (ExtractFeatures.py:175-179)."""
+    L = lib()
+    labels = _labels_2d(labels)
+    _need_cuda(labels, xs, ys)
+    H, W = labels.shape
+    n = xs.shape[0]
+    out = torch.empty(n, dtype=_I32, device=labels.device)
+    with torch.cuda.device(labels.device):
+        L.check(L.dm_points_region(_p(labels), H, W, labels.stride(0), _p(xs.contiguous()), _p(ys.contiguous()), n,
+                                   _p(out), _stream()), "dm_points_region")
+    return out
+
+
+def csr_from_region_of_point(region_of_point, n_regions):
+    """-> (offsets int64 [R+1], point_ids int32 [N_valid]), ascending point id per region."""
+    L = lib()
+    _need_cuda(region_of_point)
+    rop = region_of_point.contiguous()
+    n = rop.shape[0]
+    dev = rop.device
+    offsets = torch.empty(n_regions + 1, dtype=_I64, device=dev)
+    pids = torch.empty(max(n, 1), dtype=_I32, device=dev)
+    with torch.cuda.device(dev):
+        wsb = L.dm_csr_workspace_bytes(n, n_regions)
+        ws = torch.empty(wsb, dtype=_U8, device=dev)
+        L.check(L.dm_csr_build(_p(rop), n, n_regions, _p(offsets), _p(pids), _p(ws), wsb, _stream()), "dm_csr_build")
+    return offsets, pids
+
+
+def pool_points_csr(offsets, point_ids, feats):
+    """Mean pooling of member-point embeddings, ExtractFeatures.py:188-212 semantics
+    (membership order, sequential fp32 sum, one fp32 division) -> (sum [R,D], cnt [R])."""
+    L = lib()
+    _need_cuda(offsets, point_ids, feats)
+    if feats.dtype != _F32 or feats.dim() != 2 or feats.stride(1) != 1:
+        raise ValueError("feats must be a float32 [N, D] tensor with unit inner stride")
+    R = offsets.shape[0] - 1
+    D = feats.shape[1]
+    dev = feats.device
+    s = torch.empty((R, D), dtype=_F32, device=dev)
+    c = torch.empty(R, dtype=_I32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.dm_pool_points_csr(_p(offsets), _p(point_ids), _p(feats), feats.stride(0), R, D, _p(s), _p(c),
+                                     _stream()), "dm_pool_points_csr")
+    return s, c
+
+
+def pool_points(region_of_point, feats, n_regions):
+    """-> (sum fp32 [R,D], cnt int32 [R]) from a per-point region id."""
+    off, ids = csr_from_region_of_point(region_of_point, n_regions)
+    return pool_points_csr(off, ids, feats)
+
+
+def region_mean(sum_, cnt, only=None, out=None):
+    """-> (mean fp32 [R,D], norm2 fp32 [R]); mean = sum / max(cnt, 1)."""
+    L = lib()
+    _need_cuda(sum_, cnt)
+    R, D = sum_.shape
+    mean, n2 = out if out is not None else (torch.empty_like(sum_), torch.empty(R, dtype=_F32, device=sum_.device))
+    with torch.cuda.device(sum_.device):
+        L.check(L.dm_region_mean(_p(sum_), _p(cnt), R, D, _p(mean), _p(n2), _p(only), _stream()), "dm_region_mean")
+    return mean, n2
+
+
+def pool_dense(labels, emb, n_regions):
+    """Per-pixel embedding pooling: emb fp32 / bf16 [H,W,D] -> (sum fp32 [R,D], cnt int32 [R])."""
+    L = lib()
+    labels = _labels_2d(labels)
+    _need_cuda(labels, emb)
+    H, W = labels.shape
+    if emb.shape[:2] != labels.shape or emb.dtype not in (_F32, torch.bfloat16):
+        raise ValueError("emb must be float32 or bfloat16 [H, W, D]")
+    emb = emb.contiguous()
+    D = emb.shape[2]
+    s = torch.zeros((n_regions, D), dtype=_F32, device=labels.device)
+    c = torch.zeros(n_regions, dtype=_I32, device=labels.device)
+    with torch.cuda.device(labels.device):
+        L.check(L.dm_pool_dense(_p(labels), H, W, labels.stride(0), _p(emb), int(emb.dtype == torch.bfloat16), D,
+                                n_regions, _p(s), _p(c), _stream()), "dm_pool_dense")
+    return s, c
+
+
+def score_l2(mean, edge_keys, norm2=None):
+    """Euclidean distance between the pooled means of every edge's endpoints, the
+    reference's formula (ExtractFeatures.py:139-147) -> fp32 [E]."""
+    L = lib()
+    _need_cuda(mean, edge_keys)
+    if mean.dtype != _F32 or not mean.is_contiguous():
+        raise ValueError("mean must be a contiguous float32 [R, D] tensor")
+    R, D = mean.shape
+    dev = mean.device
+    E = edge_keys.shape[0]
+    if norm2 is None:
+        ones = torch.ones(R, dtype=_I32, device=dev)
+        _, norm2 = region_mean(mean, ones)
+    scores = torch.empty(E, dtype=_F32, device=dev)
+    with torch.cuda.device(dev):
+        n = torch.tensor([E], dtype=_I64, device=dev)
+        L.check(L.dm_score_l2(_p(mean), _p(norm2), D, _p(edge_keys.contiguous()), _p(n), E, None, _p(scores), _stream()),
+                "dm_score_l2")
+    return scores
+
+
+def relabel(labels, root):
+    """labels'[p] = root[labels[p]] (nodata kept)."""
+    L = lib()
+    labels = _labels_2d(labels)
+    _need_cuda(labels, root)
+    H, W = labels.shape
+    out = torch.empty((H, W), dtype=_I32, device=labels.device)
+    with torch.cuda.device(labels.device):
+        L.check(L.dm_relabel(_p(labels), H, W, labels.stride(0), _p(root), root.shape[0], _p(out), W, _stream()),
+                "dm_relabel")
+    return out
+
+
+def compact_roots(root):
+    """roots -> 0..R'-1 in ascending root order; returns (compact int32 [R], R')."""
+    L = lib()
+    _need_cuda(root)
+    R = root.shape[0]
+    dev = root.device
+    out = torch.empty(R, dtype=_I32, device=dev)
+    n = torch.zeros(1, dtype=_I64, device=dev)
+    with torch.cuda.device(dev):
+        wsb = L.dm_compact_roots_workspace_bytes(R)
+        ws = torch.empty(wsb, dtype=_U8, device=dev)
+        L.check(L.dm_compact_roots(_p(root), R, _p(out), _p(n), _p(ws), wsb, _stream()), "dm_compact_roots")
+    return out, int(n.item())
+
+
+@dataclass
+class MergeResult:
+    labels: torch.Tensor            # int32 [H, W] final label map (root ids)
+    root: torch.Tensor              # int32 [R]
+    rounds: int
+    merges: int
+    edge_keys: torch.Tensor         # final live edges
+    boundary_len: torch.Tensor
+    scores: torch.Tensor
+    area: torch.Tensor
+    perimeter: torch.Tensor
+    sum: torch.Tensor
+    cnt: torch.Tensor
+    rag: Optional[RAG] = None       # the initial graph
+
+
+class MergeEngine:
+    """Pre-allocated end-to-end pipeline for one raster (tile): RAG + band pooling -> point
+    pooling -> edge scoring -> iterative union-find merge -> relabel.  All buffers and
+    workspaces are allocated once; a run makes one host read-back per merge round (the
+    selected-edge count that decides whether the loop continues)."""
+
+    def __init__(self, H, W, n_regions, D, C=0, n_points=0, edge_capacity=None, device=None):
+        self.L = lib()
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.H, self.W, self.R, self.D, self.C, self.N = int(H), int(W), int(n_regions), int(D), int(C), int(n_points)
+        self.cap = default_edge_capacity(n_regions, H, W) if edge_capacity is None else int(edge_capacity)
+        self._alloc()
+
+    def _alloc(self):
+        L, dev, R, D, C, N, cap = self.L, self.dev, self.R, self.D, self.C, self.N, self.cap
+        z = lambda *s, dt: torch.zeros(*s, dtype=dt, device=dev)
+        e = lambda *s, dt: torch.empty(*s, dtype=dt, device=dev)
+        with torch.cuda.device(dev):
+            self.stats = z(2 * R + 2 * R * max(C, 1), dt=_I64)           # area | border | band_sum | band_sumsq
+            self.area, self.border = self.stats[:R], self.stats[R:2 * R]
+            self.bsum = self.stats[2 * R:2 * R + R * C].view(R, C) if C else None
+            self.bsq = self.stats[2 * R + R * max(C, 1):2 * R + R * max(C, 1) + R * C].view(R, C) if C else None
+            self.perim = e(R, dt=_I64)
+            self.keys, self.blen, self.scores = e(cap, dt=_I64), e(cap, dt=_I32), e(cap, dt=_F32)
+            self.selected = e(cap, dt=_U8)
+            self.counts = z(8, dt=_I64)       # [0..3] rag counts, [4] n_selected, [5] n_merged
+            self.host_counts = torch.zeros(8, dtype=_I64).pin_memory()
+            self.rop = e(max(N, 1), dt=_I32)
+            self.offsets, self.pids = e(R + 1, dt=_I64), e(max(N, 1), dt=_I32)
+            self.sum, self.cnt = e((R, D), dt=_F32), e(R, dt=_I32)
+            self.mean, self.norm2 = e((R, D), dt=_F32), e(R, dt=_F32)
+            self.parent = e(R, dt=_I32)
+            self.iota = torch.arange(R, dtype=_I32, device=dev)
+            self.alive, self.changed = e(R, dt=_U8), e(R, dt=_U8)
+            self.out = e((self.H, self.W), dt=_I32)
+            sizes = [L.dm_rag_workspace_bytes(cap), L.dm_csr_workspace_bytes(N, R), L.dm_merge_apply_workspace_bytes(R),
+                     L.dm_edges_rekey_workspace_bytes(cap)]
+            self.ws_bytes = max(sizes)
+            self.ws = e(self.ws_bytes, dt=_U8)
+            self.done = torch.cuda.Event()
+
+    # ---- stages -------------------------------------------------------------------------
+    def _rag(self, labels, image, rows_own, top_border, bottom_border):
+        L, s = self.L, _stream()
+        self.stats.zero_()
+        H = labels.shape[0]
+        own = H if rows_own is None else rows_own
+        L.check(L.dm_rag_build(_p(labels), own, H, self.W, labels.stride(0), _p(image), self.C, self.W * self.C, self.R,
+                               int(top_border), int(bottom_border), _p(self.area), _p(self.border), _p(self.bsum),
+                               _p(self.bsq), _p(self.keys), _p(self.blen), self.cap, _p(self.counts), _p(self.ws),
+                               self.ws_bytes, s), "dm_rag_build")
+        L.check(L.dm_perimeter(_p(self.keys), _p(self.blen), _p(self.counts), self.cap, _p(self.border), _p(self.perim),
+                               self.R, s), "dm_perimeter")
+
+    def _pool(self, labels, xs, ys, region_of_point, feats):
+        L, s = self.L, _stream()
+        N = feats.shape[0]
+        if N > self.N:
+            raise ValueError("more points than the engine was sized for")
+        if region_of_point is None:
+            L.check(L.dm_points_region(_p(labels), labels.shape[0], self.W, labels.stride(0), _p(xs), _p(ys), N,
+                                       _p(self.rop), s), "dm_points_region")
+            region_of_point = self.rop
+        L.check(L.dm_csr_build(_p(region_of_point), N, self.R, _p(self.offsets), _p(self.pids), _p(self.ws),
+                               self.ws_bytes, s), "dm_csr_build")
+        L.check(L.dm_pool_points_csr(_p(self.offsets), _p(self.pids), _p(feats), feats.stride(0), self.R, self.D,
+                                     _p(self.sum), _p(self.cnt), s), "dm_pool_points_csr")
+
+    def _read_counts(self):
+        self.host_counts.copy_(self.counts, non_blocking=True)
+        self.done.record()
+        self.done.synchronize()
+        return self.host_counts.tolist()
+
+    def load_graph(self, sum_, cnt, area, perimeter, edge_keys, boundary_len):
+        """Load an explicit region graph (e.g. the all-gathered graph of a sharded scene)."""
+        E = edge_keys.shape[0]
+        if E > self.cap:
+            self.cap = E + 1024
+            self._alloc()
+        self.sum.copy_(sum_)
+        self.cnt.copy_(cnt)
+        self.area.copy_(area)
+        self.perim.copy_(perimeter)
+        self.keys[:E].copy_(edge_keys)
+        self.blen[:E].copy_(boundary_len)
+        self.counts.zero_()
+        self.counts[0] = E
+
+    def merge_loaded_graph(self, tau, max_rounds=64):
+        with torch.cuda.device(self.dev):
+            rounds, merges = self._merge_loop(tau, max_rounds)
+            E = int(self.host_counts[0])
+        return MergeResult(None, self.parent, rounds, merges, self.keys[:E], self.blen[:E], self.scores[:E], self.area,
+                           self.perim, self.sum, self.cnt)
+
+    def run(self, labels, feats, tau, *, image=None, xs=None, ys=None, region_of_point=None, max_rounds=64,
+            rows_own=None, top_border=True, bottom_border=True, relabel=True):
+        labels = _labels_2d(labels)
+        _need_cuda(labels, feats, image, xs, ys, region_of_point)
+        if feats.dtype != _F32 or feats.dim() != 2 or feats.shape[1] != self.D or feats.stride(1) != 1:
+            raise ValueError("feats must be float32 [N, D]")
+        if (image is None) != (self.C == 0):
+            raise ValueError("engine was sized for C=%d bands" % self.C)
+        with torch.cuda.device(self.dev):
+            while True:
+                self._rag(labels, image, rows_own, top_border, bottom_border)
+                self._pool(labels, xs, ys, region_of_point, feats)
+                try:
+                    rounds, merges = self._merge_loop(tau, max_rounds)
+                    break
+                except OverflowError as ov:            # raw edge list outgrew the capacity: resize, rerun
+                    self.cap = int(ov.args[0]) + 1024
+                    self._alloc()
+            if relabel:
+                own = labels.shape[0] if rows_own is None else rows_own
+                self.L.check(self.L.dm_relabel(_p(labels), own, self.W, labels.stride(0), _p(self.parent), self.R,
+                                               _p(self.out), self.W, _stream()), "dm_relabel")
+            E = int(self.host_counts[0])
+        return MergeResult(self.out[:labels.shape[0] if rows_own is None else rows_own] if relabel else None,
+                           self.parent, rounds, merges, self.keys[:E], self.blen[:E], self.scores[:E], self.area,
+                           self.perim, self.sum, self.cnt)
+
+    def _merge_loop(self, tau, max_rounds):
+        L, s, R, D, cap = self.L, _stream(), self.R, self.D, self.cap
+        n_edges = self.counts[0:1]
+        self.parent.copy_(self.iota)
+        self.alive.fill_(1)
+        self.counts[5:8].zero_()
+        L.check(L.dm_region_mean(_p(self.sum), _p(self.cnt), R, D, _p(self.mean), _p(self.norm2), None, s), "dm_region_mean")
+        L.check(L.dm_score_l2(_p(self.mean), _p(self.norm2), D, _p(self.keys), _p(n_edges), cap, None, _p(self.scores), s),
+                "dm_score_l2")
+        rounds = merges = 0
+        while True:
+            L.check(L.dm_merge_select_l2(_p(self.scores), float(tau), _p(n_edges), cap, _p(self.selected),
+                                         self.counts[4:5].data_ptr(), s), "dm_merge_select_l2")
+            c = self._read_counts()
+            if rounds == 0:
+                if c[3] == 1:
+                    raise ValueError("labels contain ids >= n_regions")
+                if c[3] != 0:
+                    raise RuntimeError("dm_rag_build: internal pipeline error")
+                if c[2] != 0:
+                    raise OverflowError(int(c[1]))
+            merges += int(c[5])                       # members absorbed by the previous round
+            if c[4] == 0 or rounds == max_rounds:
+                break
+            rounds += 1
+            L.check(L.dm_uf_union(_p(self.parent), _p(self.keys), _p(self.selected), _p(n_edges), cap, s), "dm_uf_union")
+            L.check(L.dm_uf_compress(_p(self.parent), R, s), "dm_uf_compress")
+            L.check(L.dm_merge_apply(_p(self.parent), _p(self.alive), _p(self.changed), _p(self.sum), _p(self.cnt),
+                                     _p(self.area), _p(self.perim), R, D, self.counts[5:6].data_ptr(), _p(self.ws),
+                                     self.ws_bytes, s), "dm_merge_apply")
+            L.check(L.dm_edges_rekey(_p(self.parent), _p(self.keys), _p(self.blen), _p(self.scores), _p(n_edges), cap, R,
+                                     _p(self.perim), _p(self.ws), self.ws_bytes, s), "dm_edges_rekey")
+            L.check(L.dm_region_mean(_p(self.sum), _p(self.cnt), R, D, _p(self.mean), _p(self.norm2), _p(self.changed), s),
+                    "dm_region_mean")
+            L.check(L.dm_score_l2(_p(self.mean), _p(self.norm2), D, _p(self.keys), _p(n_edges), cap, _p(self.changed),
+                                  _p(self.scores), s), "dm_score_l2")
+        return rounds, merges
+
+
+def merge_graph(sum_, cnt, area, perimeter, edge_keys, boundary_len, tau, max_rounds=64):
+    """Merge loop on an explicit region graph (spec SURVEY.md section 8(a) R9)."""
+    _need_cuda(sum_, cnt, area, perimeter, edge_keys, boundary_len)
+    R, D = sum_.shape
+    eng = MergeEngine(1, 1, R, D, C=0, n_points=0, edge_capacity=max(edge_keys.shape[0], 1), device=sum_.device)
+    with torch.cuda.device(sum_.device):
+        eng.load_graph(sum_, cnt, area, perimeter, edge_keys, boundary_len)
+    return eng.merge_loaded_graph(tau, max_rounds)
+
+
+def merge_scene(labels, feats, tau, *, n_regions, image=None, xs=None, ys=None, region_of_point=None, max_rounds=64,
+                engine: Optional[MergeEngine] = None) -> MergeResult:
+    """End to end on one GPU: label raster (+ optional image bands) and sample-point
+    embeddings -> merged label map.  Host (CPU / numpy) inputs are staged through pinned
+    memory and the label map comes back on the host, so the call is a drop-in for a CPU
+    pipeline; CUDA inputs stay on the device."""
+    import numpy as np
+
+    host = not (isinstance(labels, torch.Tensor) and labels.is_cuda)
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def up(x, dt):
+        if x is None:
+            return None
+        t = torch.from_numpy(x) if isinstance(x, np.ndarray) else x
+        if t.dtype != dt:
+            t = t.to(dt)
+        if t.is_cuda:
+            return t
+        return t.pin_memory().to(dev, non_blocking=True)
+
+    labels_d, feats_d, image_d = up(labels, _I32), up(feats, _F32), up(image, _U8)
+    xs_d, ys_d, rop_d = up(xs, _I32), up(ys, _I32), up(region_of_point, _I32)
+    H, W = labels_d.shape
+    if engine is None:
+        engine = MergeEngine(H, W, n_regions, feats_d.shape[1], C=0 if image_d is None else image_d.shape[2],
+                             n_points=feats_d.shape[0], device=labels_d.device)
+    res = engine.run(labels_d, feats_d, tau, image=image_d, xs=xs_d, ys=ys_d, region_of_point=rop_d, max_rounds=max_rounds)
+    if host:
+        res.labels = res.labels.cpu()
+        res.root = res.root.cpu()
+    return res

@@ -1,0 +1,248 @@
+/*
+ * deepmerge_b200 -- C ABI of the B200-native DeepMerge region-merging hot path.
+ *
+ * The reference (lvxianwei/DeepMerge) is pure Python and has no FFI: its callers use
+ * plain Python callables.  "Drop-in" therefore means same-named Python callables
+ * (package deepmerge_b200) backed by this library.  Each entry
+ * point below names the reference code it replaces (file:line in /root/reference) or
+ * the SURVEY.md section 8(a) row whose written spec it implements when the reference
+ * has no code for the stage.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host;
+ *  - the caller owns every buffer including workspaces (query *_workspace_bytes, allocate,
+ *    pass); the library allocates nothing persistent and keeps no mutable global state;
+ *  - all work is enqueued on `stream` (a cudaStream_t) and is asynchronous;
+ *  - variable-size results use capacity + device-side counts: `counts` arrays live on
+ *    the device so that dependent calls chain without a host round trip;
+ *  - return value 0 = DM_OK, negative = error (dm_error_string); no exception crosses
+ *    the ABI, the library never exits the process;
+ *  - region ids are int32 in [0, n_regions); negative labels are nodata;
+ *  - an edge key is (uint64)min(u,v) << 32 | max(u,v).
+ */
+#ifndef DEEPMERGE_B200_H
+#define DEEPMERGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dm_stream_t; /* cudaStream_t */
+
+enum {
+    DM_OK = 0,
+    DM_ERR_BAD_ARG = -1,      /* null pointer, negative extent, unsupported C / D ...       */
+    DM_ERR_WORKSPACE = -2,    /* workspace smaller than *_workspace_bytes reports           */
+    DM_ERR_CUDA = -3,         /* a CUDA call failed; dm_last_cuda_error() holds the code    */
+    DM_ERR_UNSUPPORTED = -4,  /* device is not sm_100 class, or driver lacks a needed entry */
+    DM_ERR_CAPACITY = -5      /* capacity argument too small to even start                  */
+};
+
+int dm_version(void);
+const char* dm_error_string(int code);
+int dm_last_cuda_error(void);   /* cudaError_t of the last DM_ERR_CUDA on this thread */
+int dm_num_sms(void);           /* SM count of the current device (148 on B200), <0 on error */
+int64_t dm_launch_count(void);  /* kernels this library has launched in this process (all threads) */
+
+/* ----------------------------------------------------------------------------------- *
+ * Primitives (exported so that tests can pin them individually)
+ * ----------------------------------------------------------------------------------- */
+
+/* Stable LSD radix sort of (key,value) pairs on the bit range implied by n_regions
+ * (both 32-bit halves of an edge key are < n_regions).  n is read from n_dev[0] on the
+ * device, capacity bounds it.  Sorted output is left in keys/vals. */
+size_t dm_sort_edges_workspace_bytes(int64_t capacity);
+int dm_sort_edges(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t capacity,
+                  int64_t n_regions, void* ws, size_t ws_bytes, dm_stream_t stream);
+
+/* Exclusive prefix sum of uint32 -> uint32; total written to total_dev[0] (int64). */
+size_t dm_scan_workspace_bytes(int64_t capacity);
+int dm_scan_exclusive_u32(const uint32_t* in, uint32_t* out, const int64_t* n_dev, int64_t capacity,
+                          int64_t* total_dev, void* ws, size_t ws_bytes, dm_stream_t stream);
+
+/* ----------------------------------------------------------------------------------- *
+ * R1  Region adjacency graph from a label raster, fused with band pooling.
+ *     Replaces the edge list the reference READS from lines.shp
+ *     (MyUtils2.py:155-193 PolygonConnectPointDataset.add_data; LEFT_FID/RIGHT_FID,
+ *     -1 rows dropped :184-186) and the area / peri / mean* / std* attribute-table
+ *     fields it reads per polygon (MyUtils1.py:79-114).  Raster semantics: SURVEY.md
+ *     section 8(a) R1 (4-adjacency, nodata < 0 skipped).
+ *
+ * labels   int32 [rows_avail, ld]; the tile OWNS rows [0, rows_own); rows_avail is
+ *          rows_own or rows_own+1 (one halo row below, used only as lower neighbour).
+ * image    uint8 [rows_own, W, C] with row pitch image_pitch bytes, or NULL (C ignored).
+ * top_border / bottom_border: whether row 0 / row rows_own-1 touch the image border
+ *          (false for interior row tiles of a sharded scene).
+ * area, border, band_sum, band_sumsq: int64/uint64 accumulators [n_regions(,C)], ADDED to
+ *          (caller zeroes them).  border counts pixel sides facing the image border or
+ *          nodata; perimeter = border + sum of incident boundary lengths (dm_perimeter).
+ * edge_keys / boundary_len [capacity]: sorted unique edges and their pixel-pair counts.
+ * counts   int64 [4] device: [0] = E unique edges, [1] = raw per-CTA entries produced,
+ *          [2] = overflow flag (raw entries exceeded capacity: results invalid, retry
+ *          with capacity >= counts[1]), [3] = reserved.
+ * ----------------------------------------------------------------------------------- */
+size_t dm_rag_workspace_bytes(int64_t capacity);
+int dm_rag_build(const int32_t* labels, int64_t rows_own, int64_t rows_avail, int64_t W, int64_t ld,
+                 const uint8_t* image, int64_t C, int64_t image_pitch, int64_t n_regions,
+                 int top_border, int bottom_border,
+                 int64_t* area, int64_t* border, uint64_t* band_sum, uint64_t* band_sumsq,
+                 uint64_t* edge_keys, uint32_t* boundary_len, int64_t capacity, int64_t* counts,
+                 void* ws, size_t ws_bytes, dm_stream_t stream);
+
+/* The two phases of dm_rag_build, exported separately so that the raster pass (one kernel,
+ * the HBM-bound part) can be timed and profiled on its own:
+ *   dm_rag_scan   zeroes counts, runs the fused raster kernel: accumulators updated, raw
+ *                 per-CTA (key,count) entries appended inside the workspace, counts[1..3] set;
+ *   dm_rag_finish radix sort + run reduction of the raw entries -> edge_keys/boundary_len,
+ *                 counts[0].  Same ws / capacity as the scan call. */
+int dm_rag_scan(const int32_t* labels, int64_t rows_own, int64_t rows_avail, int64_t W, int64_t ld,
+                const uint8_t* image, int64_t C, int64_t image_pitch, int64_t n_regions,
+                int top_border, int bottom_border,
+                int64_t* area, int64_t* border, uint64_t* band_sum, uint64_t* band_sumsq,
+                int64_t capacity, int64_t* counts, void* ws, size_t ws_bytes, dm_stream_t stream);
+int dm_rag_finish(uint64_t* edge_keys, uint32_t* boundary_len, int64_t capacity, int64_t n_regions,
+                  int64_t* counts, void* ws, size_t ws_bytes, dm_stream_t stream);
+
+/* Sort + unique (summing lengths) an arbitrary concatenation of (key,len) lists: used to
+ * merge the per-tile lists of a sharded scene and inside the merge loop.  In place. */
+size_t dm_edges_unique_workspace_bytes(int64_t capacity);
+int dm_edges_sort_unique(uint64_t* keys, uint32_t* lens, const int64_t* n_in_dev, int64_t capacity,
+                         int64_t n_regions, int64_t* n_out_dev, void* ws, size_t ws_bytes, dm_stream_t stream);
+
+/* perimeter[r] = border[r] + sum of boundary_len over edges incident to r. */
+int dm_perimeter(const uint64_t* edge_keys, const uint32_t* boundary_len, const int64_t* n_edges_dev,
+                 int64_t capacity, const int64_t* border, int64_t* perimeter, int64_t n_regions,
+                 dm_stream_t stream);
+
+/* ----------------------------------------------------------------------------------- *
+ * R3-R5  Region -> sample-point membership and mean pooling.
+ *     dm_points_region: raster form of the PointID membership (ExtractFeatures.py:175-179):
+ *         region_of_point[i] = labels[ys[i], xs[i]]  (-1 when outside or nodata).
+ *     dm_csr_build: group point ids by region, ascending point id inside a region.
+ *     dm_pool_points_csr: ExtractFeatures.py:188-212 -- rows gathered in membership order,
+ *         sequential fp32 accumulation (np.mean(axis=0) semantics), one warp per region.
+ *         sum fp32 [R,D], cnt int32 [R].  Bit-exact with the reference's np.mean after
+ *         dm_region_mean.
+ * ----------------------------------------------------------------------------------- */
+int dm_points_region(const int32_t* labels, int64_t H, int64_t W, int64_t ld, const int32_t* xs,
+                     const int32_t* ys, int64_t n_points, int32_t* region_of_point, dm_stream_t stream);
+size_t dm_csr_workspace_bytes(int64_t n_points, int64_t n_regions);
+int dm_csr_build(const int32_t* region_of_point, int64_t n_points, int64_t n_regions, int64_t* offsets,
+                 int32_t* point_ids, void* ws, size_t ws_bytes, dm_stream_t stream);
+int dm_pool_points_csr(const int64_t* offsets, const int32_t* point_ids, const float* feats, int64_t feat_ld,
+                       int64_t n_regions, int64_t D, float* sum, int32_t* cnt, dm_stream_t stream);
+/* mean[r] = sum[r] / max(cnt[r],1) (IEEE fp32 division), norm2[r] = sum_d mean[r,d]^2.
+ * `only` (nullable) restricts the update to regions with only[r] != 0. */
+int dm_region_mean(const float* sum, const int32_t* cnt, int64_t n_regions, int64_t D, float* mean,
+                   float* norm2, const uint8_t* only, dm_stream_t stream);
+
+/* Per-pixel embedding pooling (north-star raster form of R5): emb is fp32 or bf16
+ * [H, W, D] (dtype_bf16 != 0 selects bf16); accumulates fp32 sums [R,D] and int32 counts. */
+int dm_pool_dense(const int32_t* labels, int64_t H, int64_t W, int64_t ld, const void* emb, int dtype_bf16,
+                  int64_t D, int64_t n_regions, float* sum, int32_t* cnt, dm_stream_t stream);
+
+/* ----------------------------------------------------------------------------------- *
+ * R6  Edge score = Euclidean distance between pooled means, the reference's expanded
+ *     formula sqrt(max(0,|x|^2+|y|^2-2x.y)) in fp32 (ExtractFeatures.py:119-147, called
+ *     with n=m=1 per edge at :215).  One warp per edge.
+ *     `rescore` (nullable, uint8 [R]): when given, only edges with a flagged endpoint are
+ *     recomputed; the others keep scores[e].
+ * ----------------------------------------------------------------------------------- */
+int dm_score_l2(const float* mean, const float* norm2, int64_t D, const uint64_t* edge_keys,
+                const int64_t* n_edges_dev, int64_t capacity, const uint8_t* rescore, float* scores,
+                dm_stream_t stream);
+/* Dense [n,m] distance matrix with the same formula: the Euclidean_distance(X,Y) /
+ * MC_Lyu_2020(X,Y) drop-in (ExtractFeatures.py:119, :228). */
+int dm_euclidean_matrix(const float* X, const float* Y, int64_t n, int64_t m, int64_t p, float* D,
+                        dm_stream_t stream);
+
+/* ----------------------------------------------------------------------------------- *
+ * R8  Pair-MLP scorer with the layer structure of Nets.MLP.forward (Nets.py:28-35):
+ *     three Linear + leaky_relu(0.01).  x_e = concat(mean[lo], mean[hi]) (K = 2D), hidden
+ *     H1 = H2 <= 256, out <= 16.  bf16 operands, fp32 accumulation on tcgen05 tensor cores
+ *     with TMEM accumulators.  Weights are fp32 row-major [out_features, in_features] as in
+ *     torch.nn.Linear; dm_mlp_pack converts them once into the padded bf16 UMMA layout.
+ *     o [E, n_out] fp32; h2 (nullable) [E, hidden] fp32.
+ * ----------------------------------------------------------------------------------- */
+size_t dm_mlp_packed_bytes(int64_t in_features, int64_t hidden, int64_t n_out);
+int dm_mlp_pack(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                const float* b3, int64_t in_features, int64_t hidden, int64_t n_out, void* packed,
+                dm_stream_t stream);
+int dm_score_mlp_bf16(const float* mean, int64_t D, const uint64_t* edge_keys, const int64_t* n_edges_dev,
+                      int64_t capacity, const void* packed, int64_t in_features, int64_t hidden,
+                      int64_t n_out, float* o, float* h2, dm_stream_t stream);
+/* Same network on rows of a dense matrix x [B, in_features] (the Nets.MLP()(x) drop-in). */
+int dm_mlp_forward_bf16(const float* x, int64_t B, const void* packed, int64_t in_features, int64_t hidden,
+                        int64_t n_out, float* o, float* h2, dm_stream_t stream);
+
+/* ----------------------------------------------------------------------------------- *
+ * R9  Merge loop building blocks (spec: SURVEY.md section 8(a) R9; the reference scores
+ *     edges, ExtractFeatures.py:150-225, and never merges).
+ *
+ * dm_merge_select_l2 / _mlp: flag edges with score < tau / o[e,1] > o[e,0]; counts[0] =
+ *     number selected.
+ * dm_uf_union: lock-free union over the selected edges, hooking the larger root under
+ *     the smaller (atomicCAS), so every component's root is its minimum id.
+ * dm_uf_compress: parent[x] = root(x) for all x.
+ * dm_merge_apply: for every region that stopped being a root this round: add its cnt /
+ *     area / perimeter into the root (integer atomics), emit (root, member) pairs; then
+ *     sums are accumulated per root in ASCENDING member id (sequential fp32), and
+ *     changed[root] = 1.  alive[x] is cleared for absorbed regions.
+ * dm_edges_rekey: edges -> (root(u), root(v)); self loops removed and 2*len subtracted
+ *     from perimeter[root]; result sorted + unique with lengths summed.
+ * dm_relabel: labels_out[p] = root[labels[p]] (nodata kept), 128-bit loads/stores.
+ * ----------------------------------------------------------------------------------- */
+int dm_merge_select_l2(const float* scores, float tau, const int64_t* n_edges_dev, int64_t capacity,
+                       uint8_t* selected, int64_t* n_selected_dev, dm_stream_t stream);
+int dm_merge_select_mlp(const float* o, int64_t n_out, const int64_t* n_edges_dev, int64_t capacity,
+                        uint8_t* selected, int64_t* n_selected_dev, dm_stream_t stream);
+int dm_uf_union(int32_t* parent, const uint64_t* edge_keys, const uint8_t* selected,
+                const int64_t* n_edges_dev, int64_t capacity, dm_stream_t stream);
+int dm_uf_compress(int32_t* parent, int64_t n_regions, dm_stream_t stream);
+size_t dm_merge_apply_workspace_bytes(int64_t n_regions);
+int dm_merge_apply(const int32_t* parent, uint8_t* alive, uint8_t* changed, float* sum, int32_t* cnt,
+                   int64_t* area, int64_t* perimeter, int64_t n_regions, int64_t D, int64_t* n_merged_dev,
+                   void* ws, size_t ws_bytes, dm_stream_t stream);
+size_t dm_edges_rekey_workspace_bytes(int64_t capacity);
+int dm_edges_rekey(const int32_t* parent, uint64_t* edge_keys, uint32_t* boundary_len, float* scores,
+                   int64_t* n_edges_dev, int64_t capacity, int64_t n_regions, int64_t* perimeter,
+                   void* ws, size_t ws_bytes, dm_stream_t stream);
+int dm_relabel(const int32_t* labels, int64_t H, int64_t W, int64_t ld_in, const int32_t* root,
+               int64_t n_regions, int32_t* labels_out, int64_t ld_out, dm_stream_t stream);
+/* compact[r] = rank of root(r) among roots (ascending); n_roots_dev[0] = number of roots. */
+size_t dm_compact_roots_workspace_bytes(int64_t n_regions);
+int dm_compact_roots(const int32_t* root, int64_t n_regions, int32_t* compact, int64_t* n_roots_dev,
+                     void* ws, size_t ws_bytes, dm_stream_t stream);
+
+/* ----------------------------------------------------------------------------------- *
+ * R11 Contrastive pair loss forward + backward (Losses.py:34-38):
+ *     d = sum_k (a-b)^2 ; L = mean(flag*d + (1-flag)*relu(margin-d)).
+ *     loss fp32 [1]; grad_a, grad_b fp32 [B,D] (nullable).  flag int64 as collated.
+ * ----------------------------------------------------------------------------------- */
+int dm_contrastive_fwd_bwd(const float* a, const float* b, const int64_t* flag, int64_t B, int64_t D,
+                           float margin, float* loss, float* grad_a, float* grad_b, dm_stream_t stream);
+/* Row gather used by the pair sampler path (R10): out[i] = table[idx[i]]. */
+int dm_gather_rows(const float* table, int64_t D, const int64_t* idx, int64_t n, float* out, dm_stream_t stream);
+
+/* ----------------------------------------------------------------------------------- *
+ * Synthetic scenes of SURVEY.md section 8(d), generated on the device bit-identically to
+ * oracle/oracle_np.py (bench and test utility; not part of the reference's path).
+ * ----------------------------------------------------------------------------------- */
+int dm_synth_labels(int32_t* labels, int64_t y0, int64_t rows, int64_t H, int64_t W, int64_t ld, int64_t pitch_g,
+                    uint32_t seed, dm_stream_t stream);
+int dm_synth_region_objects(int32_t* region_obj, int64_t H, int64_t W, int64_t pitch_g, uint32_t seed,
+                            dm_stream_t stream);
+int dm_synth_image(uint8_t* image, const int32_t* labels, int64_t y0, int64_t rows, int64_t W, int64_t ld,
+                   int64_t C, const int32_t* region_obj, uint32_t seed, dm_stream_t stream);
+int dm_synth_points(int32_t* xs, int32_t* ys, int64_t H, int64_t W, int64_t pitch_g, int64_t P, uint32_t seed,
+                    dm_stream_t stream);
+int dm_synth_feats(float* feats, const int32_t* region_of_point, const int32_t* region_obj, int64_t n_points,
+                   int64_t D, uint32_t seed, dm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPMERGE_B200_H */
