@@ -1,20 +1,24 @@
 // R1: region adjacency graph from a label raster, fused with per-region band pooling.
 //
-// One persistent CTA per SM walks DOWN a 256-pixel-wide column of the raster, tile by
-// tile (TH rows).  A producer warp streams label tiles (with a 1-row / 4-column halo) and
-// image tiles into a multi-stage shared-memory ring with TMA (cp.async.bulk.tensor,
-// mbarrier complete_tx); compute warps own a 128-pixel strip x BR-row band of each tile:
-// every lane owns 4 consecutive pixels (one 128-bit LDS of labels, one of image bytes)
-// and walks down the band keeping
-//   * a 2-entry register cache of per-label accumulators (area, border sides, C band sums
-//     and sums of squares computed 4 pixels at a time with PRMT + DP4A), and
-//   * a 1-entry run cache of the current (min,max) edge key with its pair count.
-// Cache evictions go to CTA-wide shared-memory hash tables (labels -> accumulators, edge
-// key -> count) that persist while the CTA walks down its column, so a region or an edge
-// costs a handful of global atomics / one appended entry per CTA instead of per pixel.
-// The appended (key,count) entries are then radix sorted and run-reduced (prims.cu).
+// Warp-autonomous streaming design.  The raster is cut into 128-pixel-wide strips; every
+// warp of a persistent grid (one 16-warp CTA per SM) owns a contiguous run of rows of one
+// strip and walks straight down it:
+//   * lane 0 of the warp feeds the warp's OWN ring of shared-memory stages with TMA
+//     (cp.async.bulk.tensor boxes of TH+1 label rows x 132 columns -- 1-row / 4-column halo
+//     -- and TH image rows), completion signalled on the warp's own mbarriers.  No producer
+//     warp, no block-level barrier anywhere after start-up: warps never wait for each other.
+//   * every lane owns 4 consecutive pixels (one 128-bit LDS of labels, one of image bytes)
+//     and keeps a 2-entry register cache of per-label accumulators: area, border sides, C
+//     band sums and sums of squares, fed 4 pixels at a time with PRMT + DP4A on byte masks.
+//     Because the warp moves down contiguous rows, a cache entry lives for the whole height
+//     of a region.  Pixel pairs straddling the two cached labels are counted with the same
+//     byte masks (no per-pair work, no divergence); a third label nearby takes a slow path.
+//   * evictions go to the warp's private shared-memory hash tables (label -> accumulators,
+//     edge key -> pair count), which are drained to global memory with 64-bit atomics /
+//     appended (key,count) entries when half full.  The appended entries are then radix
+//     sorted and run-reduced (prims.cu) into the sorted unique edge list.
 //
-// HBM traffic: labels 4 B/px + image C B/px, read once (halo re-reads hit L2).
+// HBM traffic: labels 4 B/px + image C B/px read once (halo re-reads hit L2).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,31 +30,45 @@ namespace rag {
 
 constexpr int STRIP_W = 128;            // pixels per warp row: 32 lanes x 4
 constexpr int LAB_PITCH = STRIP_W + 4;  // + halo columns (TMA inner box must be a multiple of 16 B)
-constexpr int RSLOTS = 512;             // region table slots (power of two)
-constexpr int ESLOTS = 1024;            // edge table slots (power of two)
-constexpr int MAX_PROBE = 24;
-constexpr int FLUSH_ROWS = 256;         // forced table flush period: 256 px * 256 rows * 255^2 < 2^32
+constexpr int NWARPS = 16;              // warps per CTA, each an independent pipeline
+constexpr int RS = 32;                  // region table slots per warp (power of two)
+constexpr int ES = 64;                  // edge table slots per warp (power of two)
+constexpr int RQ = 32;                  // region eviction queue entries per warp (one per lane when drained)
+constexpr int EQ = 64;                  // edge eviction queue entries per warp
+constexpr int FLUSH_ROWS = 256;         // forced drain period: 128 px * 256 rows * 255^2 < 2^32
 constexpr int EMPTY_LABEL = -1;
 constexpr unsigned long long EMPTY_KEY = ~0ull;
+constexpr int SLOT_UNKNOWN = -2, SLOT_NONE = -1;
+
+#if defined(DM_RAG_STATS) && !defined(DM_RAG_TIMING_ONLY)
+#define STAT(i) atomicAdd(&P.counters[8 + (i)], 1ull)   // counts[] must hold >= 24 entries in a stats build
+#define STAT_LAST(l, i) do { if ((l) == th.last_evicted) STAT(i); } while (0)
+#else
+#define STAT(i) ((void)0)
+#define STAT_LAST(l, i) ((void)0)
+#endif
+// stats: 7 prefetch for right, 8 second prefetch in a row, 9/10 prefetch/own-miss of the label evicted last
+// stats: 0 own-miss evict, 1 uncached add, 2 prefetch evict, 3 fast lane-rows, 4 slow lane-rows, 5 border lane-rows, 6 drains
 
 constexpr int align128(int x) { return (x + 127) / 128 * 128; }
 
-template <int C_, int TH_, int STRIPS_, int BANDS_, int STAGES_>
+template <int C_, int TH_, int NS_>
 struct Cfg {
-    static constexpr int C = C_, TH = TH_, STRIPS = STRIPS_, BANDS = BANDS_, STAGES = STAGES_;
-    static constexpr int CW = C_ > 0 ? C_ : 1;            // words of image bytes per lane-row
-    static constexpr int BR = TH / BANDS;
-    static constexpr int NCW = STRIPS * BANDS;             // compute warps
-    static constexpr int NCT = NCW * 32;                   // compute threads
-    static constexpr int THREADS = NCT + 32;               // + producer warp
-    static constexpr int TILE_W = STRIPS * STRIP_W;
+    static constexpr int C = C_, TH = TH_, NS = NS_;
+    static constexpr int CW = C_ > 0 ? C_ : 1;               // words of image bytes per lane-row
+    static constexpr int THREADS = NWARPS * 32;
     static constexpr int LAB_BOX = align128((TH + 1) * LAB_PITCH * 4);
-    static constexpr int IMG_ROW_WORDS = STRIP_W * C / 4;  // 32*C
+    static constexpr int IMG_ROW_WORDS = STRIP_W * C / 4;    // 32*C
     static constexpr int IMG_BOX = align128(TH * IMG_ROW_WORDS * 4);
-    static constexpr int STAGE_BYTES = STRIPS * (LAB_BOX + IMG_BOX);
-    static constexpr int TABLE_WORDS = RSLOTS * (3 + 2 * C) + ESLOTS * 3;
-    static constexpr int SMEM_BYTES = 128 + STAGES * STAGE_BYTES + TABLE_WORDS * 4 + 256;
-    static constexpr int FLUSH_TILES = FLUSH_ROWS / TH > 0 ? FLUSH_ROWS / TH : 1;
+    static constexpr int STAGE_BYTES = LAB_BOX + IMG_BOX;
+    static constexpr int QUEUE_WORDS = RQ * (3 + 2 * C) + EQ * 3 + 2 + 2;   // eviction queues + counts[2] + pad
+    static constexpr int TABLE_WORDS = RS * (3 + 2 * C) + ES * 3 + 2 + 2 + QUEUE_WORDS;   // + used[2] + pad
+    static constexpr int TABLE_BYTES = align128(TABLE_WORDS * 4 + NS * 8);   // + full barriers
+    static constexpr int WARP_BYTES = NS * STAGE_BYTES + TABLE_BYTES;
+    static constexpr int SMEM_BYTES = 128 + NWARPS * WARP_BYTES;
+    static constexpr int TX_BYTES = (TH + 1) * LAB_PITCH * 4 + (C > 0 ? TH * IMG_ROW_WORDS * 4 : 0);
+    static constexpr int FLUSH_UNITS = FLUSH_ROWS / TH > 0 ? FLUSH_ROWS / TH : 1;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 struct Params {
@@ -69,7 +87,7 @@ struct Params {
     uint32_t* raw_cnt;
     long long capacity;
     unsigned long long* counters;   // [1] raw entries, [2] overflow, [3] bad label / internal error
-    int tiles_x, tiles_y, tiles_per_cta;
+    int tiles_x, tiles_y, tiles_per_cta;   // strips, row blocks per strip, units per warp
 };
 
 // ------------------------------------------------------------------------------------ //
@@ -82,17 +100,14 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
     unsigned ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)   // suspend-time hint (ns): sleep in HW, do not spin
         : "memory");
     return ok != 0;
 }
@@ -100,7 +115,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity, unsigned long long* counters) {
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) {
+        if (++spins > (1u << 20)) {
             atomicExch(&counters[3], 2ull);
             __trap();
         }
@@ -113,28 +128,36 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "l"((uint64_t)map), "r"(x), "r"(y), "r"(smem_u32(bar))
         : "memory");
 }
-__device__ __forceinline__ void compute_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 // ------------------------------------------------------------------------------------ //
-// shared-memory hash tables
+// per-warp shared-memory hash tables
 // ------------------------------------------------------------------------------------ //
 template <int C>
 struct Tables {
-    int* rkey;                  // [RSLOTS]
-    unsigned* rarea;            // [RSLOTS]
-    unsigned* rborder;          // [RSLOTS]
-    unsigned* rsum;             // [C][RSLOTS]
-    unsigned* rsq;              // [C][RSLOTS]
-    unsigned long long* ekey;   // [ESLOTS]
-    unsigned* ecnt;             // [ESLOTS]
+    int* rkey;                  // [RS]
+    unsigned* rarea;            // [RS]
+    unsigned* rborder;          // [RS]
+    unsigned* rsum;             // [C][RS]
+    unsigned* rsq;              // [C][RS]
+    unsigned long long* ekey;   // [ES]
+    unsigned* ecnt;             // [ES]
     unsigned* used;             // [0] region slots used, [1] edge slots used
+    // eviction queues: lanes push evicted accumulators with plain stores; the warp drains them together
+    int* qlabel;                // [RQ]
+    unsigned* qarea;            // [RQ]
+    unsigned* qborder;          // [RQ]
+    unsigned* qsum;             // [C][RQ]
+    unsigned* qsq;              // [C][RQ]
+    unsigned long long* qekey;  // [EQ]
+    unsigned* qecnt;            // [EQ]
+    unsigned* qn;               // [0] region entries, [1] edge entries
 };
 
 __device__ __forceinline__ int region_slot(int* rkey, unsigned* used, int label) {
-    unsigned h = ((unsigned)label * 0x9E3779B1u) >> (32 - 9);
-    static_assert(RSLOTS == 512, "hash shift");
+    unsigned h = ((unsigned)label * 0x9E3779B1u) >> (32 - 5);
+    static_assert(RS == 32, "hash shift");
 #pragma unroll 1
-    for (int p = 0; p < MAX_PROBE; ++p) {
+    for (int p = 0; p < RS; ++p) {
         int k = rkey[h];
         if (k == label) return (int)h;
         if (k == EMPTY_LABEL) {
@@ -145,9 +168,9 @@ __device__ __forceinline__ int region_slot(int* rkey, unsigned* used, int label)
             }
             if (old == label) return (int)h;
         }
-        h = (h + 1) & (RSLOTS - 1);
+        h = (h + 1) & (RS - 1);
     }
-    return -1;
+    return SLOT_NONE;
 }
 
 __device__ __forceinline__ void raw_append(const Params& P, unsigned long long key, unsigned cnt) {
@@ -166,10 +189,10 @@ __device__ __forceinline__ void raw_append(const Params& P, unsigned long long k
 
 template <int C>
 __device__ __forceinline__ void edge_add(const Tables<C>& T, const Params& P, unsigned long long key, unsigned cnt) {
-    unsigned h = (((unsigned)(key >> 32) * 0x9E3779B1u) ^ ((unsigned)key * 0x85EBCA6Bu)) >> (32 - 10);
-    static_assert(ESLOTS == 1024, "hash shift");
+    unsigned h = (((unsigned)(key >> 32) * 0x9E3779B1u) ^ ((unsigned)key * 0x85EBCA6Bu)) >> (32 - 6);
+    static_assert(ES == 64, "hash shift");
 #pragma unroll 1
-    for (int p = 0; p < MAX_PROBE; ++p) {
+    for (int p = 0; p < ES / 2; ++p) {
         unsigned long long k = T.ekey[h];
         if (k == EMPTY_KEY) {
             k = atomicCAS(&T.ekey[h], EMPTY_KEY, key);
@@ -182,7 +205,7 @@ __device__ __forceinline__ void edge_add(const Tables<C>& T, const Params& P, un
             atomicAdd(&T.ecnt[h], cnt);
             return;
         }
-        h = (h + 1) & (ESLOTS - 1);
+        h = (h + 1) & (ES - 1);
     }
     raw_append(P, key, cnt);   // table saturated: straight to the global list
 }
@@ -197,6 +220,11 @@ struct Acc {
     unsigned s[C > 0 ? C : 1], q[C > 0 ? C : 1];
     __device__ __forceinline__ void reset(int l) {
         label = l;
+        area = border = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) s[c] = q[c] = 0;
+    }
+    __device__ __forceinline__ void clear() {
         area = border = 0;
 #pragma unroll
         for (int c = 0; c < C; ++c) s[c] = q[c] = 0;
@@ -221,26 +249,79 @@ __device__ __forceinline__ void global_region_add(const Params& P, int label, un
     }
 }
 
+// accumulators of one label -> the warp's region table (or straight to global when it is full)
 template <int C>
-__device__ __forceinline__ void acc_flush(const Tables<C>& T, const Params& P, Acc<C>& a) {
-    if (a.label < 0 || (a.area | a.border) == 0) return;
-    const int slot = region_slot(T.rkey, T.used, a.label);
+__device__ __forceinline__ void table_region_add(const Tables<C>& T, const Params& P, int label, unsigned area,
+                                                 unsigned border, const unsigned* s, const unsigned* q) {
+    const int slot = region_slot(T.rkey, T.used, label);
     if (slot >= 0) {
-        if (a.area) atomicAdd(&T.rarea[slot], a.area);
-        if (a.border) atomicAdd(&T.rborder[slot], a.border);
-        if (C > 0 && a.area) {
+        if (area) atomicAdd(&T.rarea[slot], area);
+        if (border) atomicAdd(&T.rborder[slot], border);
+        if (C > 0 && area) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                atomicAdd(&T.rsum[c * RSLOTS + slot], a.s[c]);
-                atomicAdd(&T.rsq[c * RSLOTS + slot], a.q[c]);
+                atomicAdd(&T.rsum[c * RS + slot], s[c]);
+                atomicAdd(&T.rsq[c * RS + slot], q[c]);
             }
         }
     } else {
-        global_region_add<C>(P, a.label, a.area, a.border, a.s, a.q);
+        global_region_add<C>(P, label, area, border, s, q);
     }
-    a.area = a.border = 0;
+}
+
+// Evicted accumulators are only PUSHED by the (few, divergent) evicting lanes; the expensive
+// hash probe + atomics happen later in drain_queues with every queued entry on its own lane.
+template <int C>
+__device__ __forceinline__ void acc_push(const Tables<C>& T, const Params& P, Acc<C>& a) {
+    if (a.label < 0 || (a.area | a.border) == 0) return;
+    const unsigned p = atomicAdd(&T.qn[0], 1u);
+    if (p < RQ) {
+        T.qlabel[p] = a.label;
+        T.qarea[p] = a.area;
+        T.qborder[p] = a.border;
 #pragma unroll
-    for (int c = 0; c < C; ++c) a.s[c] = a.q[c] = 0;
+        for (int c = 0; c < C; ++c) {
+            T.qsum[c * RQ + p] = a.s[c];
+            T.qsq[c * RQ + p] = a.q[c];
+        }
+    } else {                      // queue full (it is drained every unit): rare, do it the slow way
+        table_region_add<C>(T, P, a.label, a.area, a.border, a.s, a.q);
+    }
+    a.clear();
+}
+
+template <int C>
+__device__ __forceinline__ void edge_push(const Tables<C>& T, const Params& P, unsigned long long key, unsigned cnt) {
+    const unsigned p = atomicAdd(&T.qn[1], 1u);
+    if (p < EQ) {
+        T.qekey[p] = key;
+        T.qecnt[p] = cnt;
+    } else {
+        edge_add<C>(T, P, key, cnt);
+    }
+}
+
+// Whole warp, convergent: queued entries -> hash tables.
+template <int C>
+__device__ __forceinline__ void drain_queues(const Tables<C>& T, const Params& P, int lane) {
+    constexpr int CW = C > 0 ? C : 1;
+    __syncwarp();
+    const unsigned nr = min(T.qn[0], (unsigned)RQ), ne = min(T.qn[1], (unsigned)EQ);
+    if (nr | ne) {
+        if ((unsigned)lane < nr) {
+            unsigned s[CW], q[CW];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                s[c] = T.qsum[c * RQ + lane];
+                q[c] = T.qsq[c * RQ + lane];
+            }
+            table_region_add<C>(T, P, T.qlabel[lane], T.qarea[lane], T.qborder[lane], s, q);
+        }
+        for (unsigned k = lane; k < ne; k += 32) edge_add<C>(T, P, T.qekey[k], T.qecnt[k]);
+        __syncwarp();
+        if (lane == 0) T.qn[0] = T.qn[1] = 0;
+        __syncwarp();
+    }
 }
 
 // byte mask (0xFF per matching pixel) of the 4 pixels whose label equals L
@@ -285,35 +366,55 @@ __device__ __forceinline__ void band_transpose(const unsigned* W, unsigned* T) {
 
 template <int C>
 struct Thread {
-    Acc<C> c0, c1;
-    unsigned long long ekey;
+    Acc<C> c0, c1;              // 2-entry label cache with per-label accumulators
+    unsigned e01;               // pixel pairs seen between c0.label and c1.label (fast path)
+    unsigned long long ekey;    // 1-entry run cache of the slow path
     unsigned ecnt;
+#if defined(DM_RAG_STATS) && !defined(DM_RAG_TIMING_ONLY)
+    int last_evicted = -7;
+#endif
 
     __device__ __forceinline__ void init() {
         c0.reset(EMPTY_LABEL);
         c1.reset(EMPTY_LABEL);
+        e01 = 0;
         ekey = EMPTY_KEY;
         ecnt = 0;
     }
     __device__ __forceinline__ void edge_flush(const Tables<C>& T, const Params& P) {
-        if (ecnt) edge_add<C>(T, P, ekey, ecnt);
+        if (ecnt) edge_push<C>(T, P, ekey, ecnt);
         ecnt = 0;
     }
+    __device__ __forceinline__ void e01_flush(const Tables<C>& T, const Params& P) {
+        if (e01) edge_push<C>(T, P, pack_key(c0.label, c1.label), e01);
+        e01 = 0;
+    }
+    // replace cache entry `which` (0/1) by label l
+    __device__ __forceinline__ void evict(const Tables<C>& T, const Params& P, int which, int l) {
+#if defined(DM_RAG_STATS) && !defined(DM_RAG_TIMING_ONLY)
+        last_evicted = which == 0 ? c0.label : c1.label;
+#endif
+        e01_flush(T, P);
+        if (which == 0) {
+            acc_push<C>(T, P, c0);
+            c0.label = l;
+        } else {
+            acc_push<C>(T, P, c1);
+            c1.label = l;
+        }
+    }
     __device__ __forceinline__ void flush_all(const Tables<C>& T, const Params& P) {
-        acc_flush<C>(T, P, c0);
-        acc_flush<C>(T, P, c1);
+        e01_flush(T, P);
+        acc_push<C>(T, P, c0);
+        acc_push<C>(T, P, c1);
         edge_flush(T, P);
     }
     __device__ __forceinline__ void border_add(const Tables<C>& T, const Params& P, int v, unsigned n) {
         if (v == c0.label) c0.border += n;
         else if (v == c1.label) c1.border += n;
-        else {
-            const int slot = region_slot(T.rkey, T.used, v);
-            if (slot >= 0) atomicAdd(&T.rborder[slot], n);
-            else global_region_add<C>(P, v, 0, n, nullptr, nullptr);
-        }
+        else table_region_add<C>(T, P, v, 0, n, nullptr, nullptr);
     }
-    // a pixel pair with different labels
+    // slow path: one pixel pair with different labels
     __device__ __forceinline__ void pair(const Tables<C>& T, const Params& P, int a, int b, unsigned n) {
         if ((a | b) >= 0) {
             const unsigned long long k = pack_key(a, b);
@@ -329,6 +430,63 @@ struct Thread {
     }
 };
 
+// Drain the warp's tables to global memory (whole warp, convergent).
+template <int C>
+__device__ __forceinline__ void drain_tables(const Tables<C>& T, const Params& P, int lane) {
+    constexpr int CW = C > 0 ? C : 1;
+    static_assert(RS == 32 && ES == 64, "one / two slots per lane");
+    {
+        const int label = T.rkey[lane];
+        if (label != EMPTY_LABEL) {
+            unsigned s[CW], q[CW];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                s[c] = T.rsum[c * RS + lane];
+                q[c] = T.rsq[c * RS + lane];
+                T.rsum[c * RS + lane] = 0;
+                T.rsq[c * RS + lane] = 0;
+            }
+            global_region_add<C>(P, label, T.rarea[lane], T.rborder[lane], s, q);
+            T.rkey[lane] = EMPTY_LABEL;
+            T.rarea[lane] = 0;
+            T.rborder[lane] = 0;
+        }
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < ES; k0 += 32) {
+        const int k = k0 + lane;
+        unsigned long long key = T.ekey[k];
+        unsigned cnt = 0;
+        if (key != EMPTY_KEY) {
+            cnt = T.ecnt[k];
+            T.ekey[k] = EMPTY_KEY;
+            T.ecnt[k] = 0;
+            if ((long long)key_hi(key) >= P.n_regions) {   // label outside [0, n_regions)
+                atomicExch(&P.counters[3], 1ull);
+                key = EMPTY_KEY;
+            }
+        }
+        const bool has = key != EMPTY_KEY;
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        if (bal) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&P.counters[1], (unsigned long long)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (has) {
+                const unsigned long long idx = base + __popc(bal & lanemask_lt());
+                if ((long long)idx < P.capacity) {
+                    P.raw_keys[idx] = key;
+                    P.raw_cnt[idx] = cnt;
+                } else {
+                    atomicExch(&P.counters[2], 1ull);
+                }
+            }
+        }
+    }
+    if (lane == 0) T.used[0] = T.used[1] = 0;
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------ //
 // the kernel
 // ------------------------------------------------------------------------------------ //
@@ -336,295 +494,344 @@ template <typename CF, bool USE_TMA>
 __global__ void __launch_bounds__(CF::THREADS, 1)
 rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant__ CUtensorMap mapI, const Params P) {
     constexpr int C = CF::C;
+    constexpr int TH = CF::TH, NS = CF::NS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    unsigned char* stage_base = smem;
-    unsigned* tab = (unsigned*)(smem + CF::STAGES * CF::STAGE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* wbase = smem + (size_t)warp * CF::WARP_BYTES;       // this warp's private arena
+    unsigned* tab = (unsigned*)(wbase + NS * CF::STAGE_BYTES);
     Tables<C> T;
     T.rkey = (int*)tab;
-    T.rarea = tab + RSLOTS;
-    T.rborder = tab + 2 * RSLOTS;
-    T.rsum = tab + 3 * RSLOTS;
-    T.rsq = tab + (3 + C) * RSLOTS;
-    T.ekey = (unsigned long long*)(tab + (3 + 2 * C) * RSLOTS);
-    T.ecnt = tab + (3 + 2 * C) * RSLOTS + 2 * ESLOTS;
-    unsigned* ctrl = tab + CF::TABLE_WORDS;             // 64 words of control space
-    T.used = ctrl;                                       // [0],[1]
-    uint64_t* full_bar = (uint64_t*)(ctrl + 8);          // [STAGES]
-    uint64_t* empty_bar = full_bar + CF::STAGES;         // [STAGES]
+    T.rarea = tab + RS;
+    T.rborder = tab + 2 * RS;
+    T.rsum = tab + 3 * RS;
+    T.rsq = tab + (3 + C) * RS;
+    T.ekey = (unsigned long long*)(tab + (3 + 2 * C) * RS);
+    T.ecnt = tab + (3 + 2 * C) * RS + 2 * ES;
+    T.used = tab + (3 + 2 * C) * RS + 3 * ES;
+    {
+        unsigned* qb = T.used + 4;                                       // after used[2] + pad
+        T.qlabel = (int*)qb;
+        T.qarea = qb + RQ;
+        T.qborder = qb + 2 * RQ;
+        T.qsum = qb + 3 * RQ;
+        T.qsq = qb + (3 + C) * RQ;
+        T.qekey = (unsigned long long*)(qb + (3 + 2 * C) * RQ);
+        T.qecnt = qb + (3 + 2 * C) * RQ + 2 * EQ;
+        T.qn = qb + (3 + 2 * C) * RQ + 3 * EQ;
+    }
+    uint64_t* full_bar = (uint64_t*)(tab + ((CF::TABLE_WORDS + 1) & ~1));
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = P.tiles_x * P.tiles_y;
-    const int t_begin = min(total_tiles, (int)blockIdx.x * P.tiles_per_cta);
-    const int t_end = min(total_tiles, t_begin + P.tiles_per_cta);
-    const int my_tiles = t_end - t_begin;
+    // ---- this warp's run of units (unit = TH rows of one strip, column-major order) -------
+    const long long total_units = (long long)P.tiles_x * P.tiles_y;
+    const long long gw = (long long)blockIdx.x * NWARPS + warp;
+    const long long u_begin = min(total_units, gw * (long long)P.tiles_per_cta);
+    const long long u_end = min(total_units, u_begin + P.tiles_per_cta);
+    const int my_units = (int)(u_end - u_begin);
 
-    // ---- init -------------------------------------------------------------------------
-    for (int i = threadIdx.x; i < RSLOTS; i += CF::THREADS) {
-        T.rkey[i] = EMPTY_LABEL;
-        T.rarea[i] = 0;
-        T.rborder[i] = 0;
+    // ---- init (warp-private, no block barrier needed) ---------------------------------------
+    T.rkey[lane] = EMPTY_LABEL;
+    T.rarea[lane] = 0;
+    T.rborder[lane] = 0;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            T.rsum[c * RSLOTS + i] = 0;
-            T.rsq[c * RSLOTS + i] = 0;
-        }
+    for (int c = 0; c < C; ++c) {
+        T.rsum[c * RS + lane] = 0;
+        T.rsq[c * RS + lane] = 0;
     }
-    for (int i = threadIdx.x; i < ESLOTS; i += CF::THREADS) {
-        T.ekey[i] = EMPTY_KEY;
-        T.ecnt[i] = 0;
-    }
-    if (threadIdx.x == 0) {
+    T.ekey[lane] = EMPTY_KEY;
+    T.ekey[lane + 32] = EMPTY_KEY;
+    T.ecnt[lane] = 0;
+    T.ecnt[lane + 32] = 0;
+    if (lane == 0) {
         T.used[0] = T.used[1] = 0;
+        T.qn[0] = T.qn[1] = 0;
         if (USE_TMA) {
-            for (int s = 0; s < CF::STAGES; ++s) {
-                mbar_init(&full_bar[s], 1);
-                mbar_init(&empty_bar[s], CF::NCW);
-            }
+            for (int s = 0; s < NS; ++s) mbar_init(&full_bar[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
-    __syncthreads();
+    __syncwarp();
+    if (my_units == 0) return;
 
-    if (warp == CF::NCW) {
-        // ================================ producer warp ================================
-        if (USE_TMA && lane == 0) {
-            for (int i = 0; i < my_tiles; ++i) {
-                const int t = t_begin + i;
-                const int tx = t / P.tiles_y, ty = t - tx * P.tiles_y;
-                const int st = i % CF::STAGES;
-                const unsigned ph = (unsigned)(i / CF::STAGES) & 1u;
-                mbar_wait(&empty_bar[st], ph ^ 1u, P.counters);
-                int strips = 0;
-#pragma unroll
-                for (int s = 0; s < CF::STRIPS; ++s) strips += (tx * CF::TILE_W + s * STRIP_W < P.W) ? 1 : 0;
-                mbar_expect_tx(&full_bar[st], (unsigned)(strips * ((CF::TH + 1) * LAB_PITCH * 4 +
-                                                                   (C > 0 ? CF::TH * CF::IMG_ROW_WORDS * 4 : 0))));
-                unsigned char* sb = stage_base + (size_t)st * CF::STAGE_BYTES;
-#pragma unroll
-                for (int s = 0; s < CF::STRIPS; ++s) {
-                    const int x0 = tx * CF::TILE_W + s * STRIP_W;
-                    if (x0 < P.W) {
-                        tma_load_2d(sb + s * CF::LAB_BOX, &mapL, x0, ty * CF::TH, &full_bar[st]);
-                        if (C > 0)
-                            tma_load_2d(sb + CF::STRIPS * CF::LAB_BOX + s * CF::IMG_BOX, &mapI, x0 * C / 4, ty * CF::TH,
-                                        &full_bar[st]);
-                    }
-                }
-            }
-        }
-        return;
+    auto issue = [&](int k) {     // lane 0: TMA loads of this warp's k-th unit into stage k % NS
+        const long long u = u_begin + k;
+        const int sx = (int)(u / P.tiles_y), j = (int)(u - (long long)sx * P.tiles_y);
+        const int st = k % NS;
+        unsigned char* sb = wbase + (size_t)st * CF::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[st], (unsigned)CF::TX_BYTES);
+        tma_load_2d(sb, &mapL, sx * STRIP_W, j * TH, &full_bar[st]);
+        if (C > 0) tma_load_2d(sb + CF::LAB_BOX, &mapI, sx * STRIP_W * C / 4, j * TH, &full_bar[st]);
+    };
+    if (USE_TMA && lane == 0) {
+        for (int k = 0; k < NS && k < my_units; ++k) issue(k);
     }
 
-    // ================================== compute warps ==================================
-    const int strip = warp % CF::STRIPS, band = warp / CF::STRIPS;
+#ifdef DM_RAG_STATS
+    unsigned long long t_start;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+#endif
     Thread<C> th;
     th.init();
-    int tiles_since_flush = 0;
+    int units_since_drain = 0;
+    int4 own = make_int4(0, 0, 0, 0);
+    unsigned m0 = 0, m1 = 0;
+    bool have_masks = false;            // m0/m1 valid for `own` against the current cache labels
+    bool use0 = false, use1 = false;    // cache entry touched during the current unit (see the GC below)
+    // (strip, row block) of the current unit, advanced incrementally (column-major order)
+    int sx = (int)(u_begin / P.tiles_y), j = (int)(u_begin - (long long)sx * P.tiles_y);
+    bool contiguous = false;
 
-    for (int i = 0; i < my_tiles; ++i) {
-        const int t = t_begin + i;
-        const int tx = t / P.tiles_y, ty = t - tx * P.tiles_y;
-        const int st = USE_TMA ? i % CF::STAGES : 0;
-        unsigned char* sb = stage_base + (size_t)st * CF::STAGE_BYTES;
-        const int tile_x0 = tx * CF::TILE_W, tile_y0 = ty * CF::TH;
-
+    for (int i = 0; i < my_units; ++i) {
+        const int st = USE_TMA ? i % NS : 0;
+        unsigned char* sb = wbase + (size_t)st * CF::STAGE_BYTES;
+        const int strip_x0 = sx * STRIP_W, unit_y0 = j * TH;
+        int* Lw = (int*)sb;
         if (USE_TMA) {
-            mbar_wait(&full_bar[st], (unsigned)(i / CF::STAGES) & 1u, P.counters);
+            mbar_wait(&full_bar[st], (unsigned)(i / NS) & 1u, P.counters);
         } else {
             // fallback staging for rasters whose pitch/base TMA cannot describe
-            for (int s = 0; s < CF::STRIPS; ++s) {
-                int* L = (int*)(sb + s * CF::LAB_BOX);
-                const int x0 = tile_x0 + s * STRIP_W;
-                for (int k = threadIdx.x; k < (CF::TH + 1) * LAB_PITCH; k += CF::NCT) {
-                    const int r = k / LAB_PITCH, cidx = k - r * LAB_PITCH;
-                    const int gy = tile_y0 + r, gx = x0 + cidx;
-                    L[k] = (gy < P.rows_avail && gx < P.W) ? P.labels[(int64_t)gy * P.ld + gx] : 0;
-                }
-                if constexpr (C > 0) {
-                    unsigned char* I = sb + CF::STRIPS * CF::LAB_BOX + s * CF::IMG_BOX;
-                    for (int k = threadIdx.x; k < CF::TH * CF::IMG_ROW_WORDS * 4; k += CF::NCT) {
-                        const int r = k / (CF::IMG_ROW_WORDS * 4), bidx = k - r * (CF::IMG_ROW_WORDS * 4);
-                        const int gy = tile_y0 + r;
-                        const int64_t gb = (int64_t)x0 * C + bidx;
-                        I[k] = (gy < P.rows_own && gb < (int64_t)P.W * C) ? P.image[(int64_t)gy * P.image_pitch + gb] : 0;
-                    }
-                }
-            }
-            compute_bar(CF::NCT);
-        }
-
-        const int x0 = tile_x0 + strip * STRIP_W + 4 * lane;   // first of this lane's 4 pixels
-        if (tile_x0 + strip * STRIP_W < P.W) {
-            const int* L = (const int*)(sb + strip * CF::LAB_BOX);
-            const unsigned* I = (const unsigned*)(sb + CF::STRIPS * CF::LAB_BOX + strip * CF::IMG_BOX);
-            const int nin = min(4, max(0, P.W - x0));          // pixels of this lane inside the image
-            const int r0 = band * CF::BR;
-            int4 own = *(const int4*)(L + r0 * LAB_PITCH + 4 * lane);
-#pragma unroll 1
-            for (int r = r0; r < r0 + CF::BR; ++r) {
-                const int y = tile_y0 + r;
-                if (y >= P.rows_own) break;
-                const int4 dn = *(const int4*)(L + (r + 1) * LAB_PITCH + 4 * lane);
-                int right = __shfl_down_sync(0xffffffffu, own.x, 1);
-                if (lane == 31) right = L[r * LAB_PITCH + STRIP_W];
-                unsigned W[CF::CW], TB[CF::CW];
-                if (C > 0) {
-                    if (C == 4) {
-                        const uint4 v = *(const uint4*)(I + r * CF::IMG_ROW_WORDS + 4 * lane);
-                        W[0] = v.x; W[1 % CF::CW] = v.y; W[2 % CF::CW] = v.z; W[3 % CF::CW] = v.w;
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < C; ++c) W[c] = I[r * CF::IMG_ROW_WORDS + C * lane + c];
-                    }
-                    band_transpose<C>(W, TB);
-                }
-                int4 a = own;
-                const bool interior = (nin == 4) && (x0 + 4 < P.W) && (x0 > 0) && (y > 0) && (y + 1 < P.rows_avail);
-                if (!interior) {   // out-of-image pixels behave like "no pixel": never counted, never paired
-                    if (nin < 4) a.w = EMPTY_LABEL;
-                    if (nin < 3) a.z = EMPTY_LABEL;
-                    if (nin < 2) a.y = EMPTY_LABEL;
-                    if (nin < 1) a.x = EMPTY_LABEL;
-                }
-                // ---- accumulate the 4 pixels into the 2-entry label cache -----------------
-                unsigned m0 = match4(a, th.c0.label), m1 = match4(a, th.c1.label);
-                unsigned covered = m0 | m1 | neg4(a);
-                while (covered != 0xffffffffu) {               // rare: a label outside the cache
-                    const int i4 = (__ffs(~covered) - 1) >> 3;
-                    const int Lb = pick4(a, i4);
-                    if (m0 == 0 || th.c0.label < 0) {
-                        acc_flush<C>(T, P, th.c0);
-                        th.c0.reset(Lb);
-                        m0 = match4(a, Lb);
-                        covered |= m0;
-                    } else if (m1 == 0 || th.c1.label < 0) {
-                        acc_flush<C>(T, P, th.c1);
-                        th.c1.reset(Lb);
-                        m1 = match4(a, Lb);
-                        covered |= m1;
-                    } else {                                   // >2 labels in 4 pixels: uncached add
-                        Acc<C> one;
-                        one.reset(Lb);
-                        const unsigned bm = 0xffu << (8 * i4);
-                        acc_pixels<C>(one, bm, TB);
-                        acc_flush<C>(T, P, one);
-                        covered |= bm;
-                    }
-                }
-                acc_pixels<C>(th.c0, m0, TB);
-                acc_pixels<C>(th.c1, m1, TB);
-                // ---- neighbour pairs ----------------------------------------------------------
-                if (interior) {
-                    if (a.x != a.y) th.pair(T, P, a.x, a.y, 1);
-                    if (a.y != a.z) th.pair(T, P, a.y, a.z, 1);
-                    if (a.z != a.w) th.pair(T, P, a.z, a.w, 1);
-                    if (a.w != right) th.pair(T, P, a.w, right, 1);
-                    const bool urow = (a.x == a.y) & (a.y == a.z) & (a.z == a.w);
-                    const bool udn = (dn.x == dn.y) & (dn.y == dn.z) & (dn.z == dn.w);
-                    if (urow & udn) {
-                        if (a.x != dn.x) th.pair(T, P, a.x, dn.x, 4);
-                    } else {
-                        if (a.x != dn.x) th.pair(T, P, a.x, dn.x, 1);
-                        if (a.y != dn.y) th.pair(T, P, a.y, dn.y, 1);
-                        if (a.z != dn.z) th.pair(T, P, a.z, dn.z, 1);
-                        if (a.w != dn.w) th.pair(T, P, a.w, dn.w, 1);
-                    }
-                } else if (nin > 0) {
-                    // image borders, partial lanes, first/last rows: pixel by pixel
-                    const bool has_dn = (y + 1 < P.rows_avail);
-                    const bool top = (y == 0) && P.top_border;
-                    const bool bot = (!has_dn) && (y == P.rows_own - 1) && P.bottom_border;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (k < nin) {
-                            const int l = pick4(a, k);
-                            const int x = x0 + k;
-                            if (x + 1 < P.W) {
-                                const int rn = (k == 3) ? right : pick4(a, k + 1);
-                                if (l != rn) th.pair(T, P, l, rn, 1);
-                            } else if (l >= 0) {
-                                th.border_add(T, P, l, 1);      // right image border
-                            }
-                            if (x == 0 && l >= 0) th.border_add(T, P, l, 1);
-                            if (has_dn) {
-                                const int d = pick4(dn, k);
-                                if (l != d) th.pair(T, P, l, d, 1);
-                            } else if (bot && l >= 0) {
-                                th.border_add(T, P, l, 1);
-                            }
-                            if (top && l >= 0) th.border_add(T, P, l, 1);
-                        }
-                    }
-                }
-                own = dn;
-            }
-        }
-        th.flush_all(T, P);
-        if (USE_TMA) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[st]);
+            for (int k = lane; k < (TH + 1) * LAB_PITCH; k += 32) {
+                const int r = k / LAB_PITCH, cidx = k - r * LAB_PITCH;
+                const int gy = unit_y0 + r, gx = strip_x0 + cidx;
+                Lw[k] = (gy < P.rows_avail && gx < P.W) ? P.labels[(int64_t)gy * P.ld + gx] : 0;
+            }
+            if constexpr (C > 0) {
+                unsigned char* Ib = sb + CF::LAB_BOX;
+                for (int k = lane; k < TH * CF::IMG_ROW_WORDS * 4; k += 32) {
+                    const int r = k / (CF::IMG_ROW_WORDS * 4), bidx = k - r * (CF::IMG_ROW_WORDS * 4);
+                    const int gy = unit_y0 + r;
+                    const int64_t gb = (int64_t)strip_x0 * C + bidx;
+                    Ib[k] = (gy < P.rows_own && gb < (int64_t)P.W * C) ? P.image[(int64_t)gy * P.image_pitch + gb] : 0;
+                }
+            }
+            __syncwarp();
         }
 
-        // ---- table maintenance (all compute warps) -----------------------------------------
-        ++tiles_since_flush;
-        compute_bar(CF::NCT);
-        const bool need = (T.used[0] > RSLOTS / 2) || (T.used[1] > ESLOTS / 2) || (tiles_since_flush >= CF::FLUSH_TILES) ||
-                          (i + 1 == my_tiles);
-        compute_bar(CF::NCT);
-        if (need) {
-            for (int k = threadIdx.x; k < RSLOTS; k += CF::NCT) {
-                const int label = T.rkey[k];
-                if (label != EMPTY_LABEL) {
-                    unsigned s[CF::CW], q[CF::CW];
+        const int* L = Lw;
+        const unsigned* I = (const unsigned*)(sb + CF::LAB_BOX);
+        const int x0 = strip_x0 + 4 * lane;                 // first of this lane's 4 pixels
+        const int nin = min(4, max(0, P.W - x0));           // pixels of this lane inside the image
+        // Image borders without a separate code path: pixels right of the image are replaced by
+        // copies of the row's last pixel (so they never differ from a neighbour) and masked out of
+        // the accumulation with `vm`; border sides are added arithmetically below.
+        const unsigned vm = nin >= 4 ? 0xffffffffu : ((1u << (8 * nin)) - 1u);
+        const bool left_edge = (x0 == 0);
+        const int last_k = P.W - 1 - x0;                    // in [0,3] for the lane holding the last column
+        const int last_col = P.W - 1 - strip_x0;            // < STRIP_W only in the last strip
+        if (!contiguous) {                                  // new strip / first unit: nothing carried over
+            own = *(const int4*)(L + 4 * lane);
+            if (nin < 4) {
+                const int e = L[min(last_col, STRIP_W - 1)];
+                if (nin < 1) own.x = e;
+                if (nin < 2) own.y = e;
+                if (nin < 3) own.z = e;
+                own.w = e;
+            }
+            have_masks = false;
+        }
+#pragma unroll 1
+        for (int r = 0; r < TH; ++r) {
+            const int y = unit_y0 + r;
+            if (y >= P.rows_own) break;
+            const bool has_dn = (y + 1 < P.rows_avail);     // warp-uniform
+            int4 dn = *(const int4*)(L + (r + 1) * LAB_PITCH + 4 * lane);
+            int right = __shfl_down_sync(0xffffffffu, own.x, 1);
+            if (lane == 31) right = L[r * LAB_PITCH + STRIP_W];
+            if (nin < 4) {                                  // only lanes of the last strip
+                const int e = L[(r + 1) * LAB_PITCH + min(last_col, STRIP_W - 1)];
+                if (nin < 1) dn.x = e;
+                if (nin < 2) dn.y = e;
+                if (nin < 3) dn.z = e;
+                dn.w = e;
+            }
+            if (!has_dn) dn = own;                          // last raster row: no vertical pairs
+            if (x0 + 4 >= P.W) right = own.w;               // nothing to the right of the last column
+            unsigned W[CF::CW], TB[CF::CW];
+            if (C > 0) {
+                if (C == 4) {
+                    const uint4 v = *(const uint4*)(I + r * CF::IMG_ROW_WORDS + 4 * lane);
+                    W[0] = v.x; W[1 % CF::CW] = v.y; W[2 % CF::CW] = v.z; W[3 % CF::CW] = v.w;
+                } else {
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        s[c] = T.rsum[c * RSLOTS + k];
-                        q[c] = T.rsq[c * RSLOTS + k];
-                        T.rsum[c * RSLOTS + k] = 0;
-                        T.rsq[c * RSLOTS + k] = 0;
-                    }
-                    global_region_add<C>(P, label, T.rarea[k], T.rborder[k], s, q);
-                    T.rkey[k] = EMPTY_LABEL;
-                    T.rarea[k] = 0;
-                    T.rborder[k] = 0;
+                    for (int c = 0; c < C; ++c) W[c] = I[r * CF::IMG_ROW_WORDS + C * lane + c];
+                }
+                band_transpose<C>(W, TB);
+            }
+            const int4 a = own;
+            // ---- the 4 pixels go into the 2-entry label cache ------------------------------
+            if (!have_masks) {
+                m0 = match4(a, th.c0.label);
+                m1 = match4(a, th.c1.label);
+            }
+            const bool any_neg = (a.x | a.y | a.z | a.w | right | dn.x | dn.y | dn.z | dn.w) < 0;
+            unsigned covered = m0 | m1;
+            if (any_neg) covered |= neg4(a);
+            // side counts of this row that face the image border (left / right column, first / last row)
+            const bool top_row = (y == 0) && P.top_border;
+            const bool bot_row = (!has_dn) && (y == P.rows_own - 1) && P.bottom_border;
+            while (covered != 0xffffffffu) {               // a label outside the cache
+                const int i4 = (__ffs(~covered) - 1) >> 3;
+                const int Lb = pick4(a, i4);
+                if (m0 == 0 || th.c0.label < 0) {
+                    STAT(0);
+                    STAT_LAST(Lb, 10);
+                    th.evict(T, P, 0, Lb);
+                    m0 = match4(a, Lb);
+                    covered |= m0;
+                } else if (m1 == 0 || th.c1.label < 0) {
+                    STAT(0);
+                    STAT_LAST(Lb, 10);
+                    th.evict(T, P, 1, Lb);
+                    m1 = match4(a, Lb);
+                    covered |= m1;
+                } else {                                   // >2 labels in 4 pixels: uncached add
+                    STAT(1);
+                    Acc<C> one;
+                    one.reset(Lb);
+                    const unsigned bm = (0xffu << (8 * i4)) & vm;
+                    acc_pixels<C>(one, bm, TB);
+                    if (bm) one.border = (left_edge && i4 == 0 ? 1u : 0u) + (i4 == last_k ? 1u : 0u) + (top_row ? 1u : 0u) +
+                                         (bot_row ? 1u : 0u);
+                    acc_push<C>(T, P, one);
+                    covered |= 0xffu << (8 * i4);
                 }
             }
-            for (int k0 = 0; k0 < ESLOTS; k0 += CF::NCT) {
-                const int k = k0 + threadIdx.x;
-                unsigned long long key = k < ESLOTS ? T.ekey[k] : EMPTY_KEY;
-                unsigned cnt = 0;
-                if (key != EMPTY_KEY) {
-                    cnt = T.ecnt[k];
-                    T.ekey[k] = EMPTY_KEY;
-                    T.ecnt[k] = 0;
-                    if ((long long)key_hi(key) >= P.n_regions) {   // label outside [0, n_regions)
-                        atomicExch(&P.counters[3], 1ull);
-                        key = EMPTY_KEY;
-                    }
+            if (any_neg) {                                 // cache labels are >= 0 or EMPTY(-1): keep nodata out
+                const unsigned ok = ~neg4(a);
+                m0 &= ok;
+                m1 &= ok;
+            }
+            {
+                const unsigned v0 = m0 & vm, v1 = m1 & vm;
+                acc_pixels<C>(th.c0, v0, TB);
+                acc_pixels<C>(th.c1, v1, TB);
+                if (left_edge) {
+                    th.c0.border += v0 & 1u;
+                    th.c1.border += v1 & 1u;
                 }
-                const bool has = key != EMPTY_KEY;
-                const unsigned bal = __ballot_sync(0xffffffffu, has);
-                if (bal) {
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(&P.counters[1], (unsigned long long)__popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (has) {
-                        const unsigned long long idx = base + __popc(bal & lanemask_lt());
-                        if ((long long)idx < P.capacity) {
-                            P.raw_keys[idx] = key;
-                            P.raw_cnt[idx] = cnt;
-                        } else {
-                            atomicExch(&P.counters[2], 1ull);
-                        }
-                    }
+                if ((unsigned)last_k < 4u) {
+                    th.c0.border += (v0 >> (8 * last_k)) & 1u;
+                    th.c1.border += (v1 >> (8 * last_k)) & 1u;
+                }
+                if (top_row | bot_row) {                    // warp-uniform
+                    const unsigned n = (top_row ? 1u : 0u) + (bot_row ? 1u : 0u);
+                    th.c0.border += n * (__popc(v0) >> 3);
+                    th.c1.border += n * (__popc(v1) >> 3);
                 }
             }
-            if (threadIdx.x == 0) T.used[0] = T.used[1] = 0;
-            tiles_since_flush = 0;
-            compute_bar(CF::NCT);
+            // ---- neighbour pairs -------------------------------------------------------------
+            // masks of the lower row against the same two labels: reused as the next row's m0/m1
+            unsigned d0 = match4(dn, th.c0.label), d1 = match4(dn, th.c1.label);
+            bool r0m = right == th.c0.label, r1m = right == th.c1.label;
+            const bool own_ok = !any_neg && ((m0 | m1) == 0xffffffffu);   // 4 pixels fully cached, no nodata around
+            bool nbr_ok = ((d0 | d1) == 0xffffffffu) && (r0m | r1m);
+            if (own_ok && !nbr_ok) {
+                // a neighbour label that is not cached (a boundary running along this lane's edge,
+                // or the region that starts in the next row): bring it into a cache entry none of
+                // this row's pixels use, so that the row still takes the convergent path below
+#pragma unroll 1
+                for (int tries = 0; tries < 2; ++tries) {
+                    const unsigned dcov = d0 | d1;
+                    int cand;
+                    if (!(r0m | r1m)) cand = right;
+                    else if (dcov != 0xffffffffu) cand = pick4(dn, (__ffs(~dcov) - 1) >> 3);
+                    else break;
+                    if (m0 == 0) th.evict(T, P, 0, cand);
+                    else if (m1 == 0) th.evict(T, P, 1, cand);
+                    else break;                            // three labels meet here: slow path
+                    STAT(2);
+                    if (cand == right) STAT(7);
+                    if (tries == 1) STAT(8);
+                    STAT_LAST(cand, 9);
+                    d0 = match4(dn, th.c0.label);
+                    d1 = match4(dn, th.c1.label);
+                    r0m = right == th.c0.label;
+                    r1m = right == th.c1.label;
+                }
+                nbr_ok = ((d0 | d1) == 0xffffffffu) && (r0m | r1m);
+            }
+            use0 |= (m0 | d0) != 0 || r0m;
+            use1 |= (m1 | d1) != 0 || r1m;
+            if (own_ok && nbr_ok) {
+                // every label around is one of the two cached ones: pairs that straddle them are
+                // counted with byte-mask logic, no per-pair work and no divergence
+                const unsigned n0 = (m0 >> 8) | (r0m ? 0xff000000u : 0u);
+                const unsigned n1 = (m1 >> 8) | (r1m ? 0xff000000u : 0u);
+                const unsigned cross_h = (m0 & n1) | (m1 & n0);
+                const unsigned cross_v = ((m0 & d1) | (m1 & d0)) & vm;      // padded copies right of the image do not pair
+                th.e01 += (__popc(cross_h) + __popc(cross_v)) >> 3;
+                STAT(3);
+            } else {
+                // a third label or nodata nearby: the 8 pairs one by one (bits 0-3 = (x,x+1), 4-7 = (y,y+1))
+                unsigned pm = (a.x != a.y ? 1u : 0u) | (a.y != a.z ? 2u : 0u) | (a.z != a.w ? 4u : 0u) |
+                              (a.w != right ? 8u : 0u) | (a.x != dn.x ? 16u : 0u) | (a.y != dn.y ? 32u : 0u) |
+                              (a.z != dn.z ? 64u : 0u) | (a.w != dn.w ? 128u : 0u);
+                pm &= 0x0fu | (((1u << nin) - 1u) << 4);                    // no vertical pairs right of the image
+                STAT(4);
+                while (pm) {
+                    const int b = __ffs(pm) - 1;
+                    pm &= pm - 1;
+                    const int k = b & 3;
+                    const int pa = pick4(a, k);
+                    const int pb = b < 4 ? (k == 0 ? a.y : k == 1 ? a.z : k == 2 ? a.w : right) : pick4(dn, k);
+                    th.pair(T, P, pa, pb, 1);
+                }
+            }
+            own = dn;
+            m0 = d0;
+            m1 = d1;
+            have_masks = !any_neg;
+        }
+
+        // ---- convergent garbage collection of the label cache --------------------------------------
+        // An entry nothing touched during this unit is pushed out now, by all lanes together, so
+        // that the next miss of such a lane finds an empty entry instead of evicting on its own.
+        if ((!use0 && th.c0.label >= 0) || (!use1 && th.c1.label >= 0)) {
+            th.e01_flush(T, P);
+            if (!use0 && th.c0.label >= 0) {
+                acc_push<C>(T, P, th.c0);
+                th.c0.label = EMPTY_LABEL;
+            }
+            if (!use1 && th.c1.label >= 0) {
+                acc_push<C>(T, P, th.c1);
+                th.c1.label = EMPTY_LABEL;
+            }
+        }
+        use0 = use1 = false;
+        // next unit of this warp's run
+        contiguous = (j + 1 < P.tiles_y);
+        if (contiguous) ++j;
+        else { j = 0; ++sx; }
+
+        // ---- recycle the stage: this warp is its only reader, so it refills it itself ----------
+        __syncwarp();
+        if (USE_TMA && lane == 0 && i + NS < my_units) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before async writes
+            issue(i + NS);
+        }
+
+        // ---- queued evictions -> tables (whole warp, every unit); tables -> global when they fill up ----
+        ++units_since_drain;
+        const bool last = (i + 1 == my_units);
+        const bool forced = units_since_drain >= CF::FLUSH_UNITS || last;
+        if (forced) th.flush_all(T, P);
+        drain_queues<C>(T, P, lane);
+        const unsigned ur = T.used[0], ue = T.used[1];
+        if (ur > RS / 2 || ue > ES / 2 || forced) {
+            if (lane == 0) STAT(6);
+            drain_tables<C>(T, P, lane);
+            units_since_drain = 0;
         }
     }
+#ifdef DM_RAG_STATS
+    if (lane == 0) {       // per-warp wall time (ns): counts[] must hold 32 + 2 * total_warps entries
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        P.counters[32 + 2 * gw] = t_start;
+        P.counters[32 + 2 * gw + 1] = t_end;
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------ //
@@ -648,53 +855,27 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+static thread_local int g_last_path = -1;     // 1 = TMA staging, 0 = ld.global staging
+static thread_local int g_last_encode_error = 0;
+int last_path() { return g_last_path; }
+int last_encode_error() { return g_last_encode_error; }
+
 static bool make_map_2d(CUtensorMap* m, const void* base, uint64_t dim0, uint64_t dim1, uint64_t pitch_bytes,
                         uint32_t box0, uint32_t box1) {
     EncodeTiledFn enc = get_encode();
-    if (!enc) return false;
+    if (!enc) {
+        g_last_encode_error = -1;
+        return false;
+    }
     cuuint64_t dims[2] = {dim0, dim1};
     cuuint64_t strides[1] = {pitch_bytes};
     cuuint32_t box[2] = {box0, box1};
     cuuint32_t estr[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-template <typename CF>
-static int launch(const Params& Pin, bool allow_tma, cudaStream_t s) {
-    Params P = Pin;
-    P.tiles_x = (int)ceil_div(P.W, CF::TILE_W);
-    P.tiles_y = (int)ceil_div(P.rows_own, CF::TH);
-    const int total = P.tiles_x * P.tiles_y;
-    if (total == 0) return DM_OK;
-    const int grid = min(total, num_sms());
-    P.tiles_per_cta = (int)ceil_div(total, grid);
-    const int grid2 = (int)ceil_div(total, P.tiles_per_cta);
-
-    CUtensorMap mapL, mapI;
-    memset(&mapL, 0, sizeof(mapL));
-    memset(&mapI, 0, sizeof(mapI));
-    // TMA needs 16-byte aligned bases and row pitches; anything else takes the ld.global staging path
-    bool tma = allow_tma && ((uintptr_t)P.labels % 16 == 0) && ((P.ld * 4) % 16 == 0) && P.ld >= P.W;
-    if (CF::C > 0)
-        tma = tma && ((uintptr_t)P.image % 16 == 0) && (P.image_pitch % 16 == 0) && (((int64_t)P.W * CF::C) % 4 == 0);
-    if (tma)
-        tma = make_map_2d(&mapL, P.labels, (uint64_t)P.W, (uint64_t)P.rows_avail, (uint64_t)P.ld * 4, LAB_PITCH, CF::TH + 1);
-    if (tma && CF::C > 0)
-        tma = make_map_2d(&mapI, P.image, (uint64_t)P.W * CF::C / 4, (uint64_t)P.rows_own, (uint64_t)P.image_pitch,
-                          CF::IMG_ROW_WORDS, CF::TH);
-    if (tma) {
-        auto k = rag_pool_kernel<CF, true>;
-        DM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
-        DM_COUNT_LAUNCH(); k<<<grid2, CF::THREADS, CF::SMEM_BYTES, s>>>(mapL, mapI, P);
-    } else {
-        auto k = rag_pool_kernel<CF, false>;
-        DM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
-        DM_COUNT_LAUNCH(); k<<<grid2, CF::THREADS, CF::SMEM_BYTES, s>>>(mapL, mapI, P);
-    }
-    DM_LAUNCH_CHECK();
-    return DM_OK;
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    g_last_encode_error = (int)r;
+    return r == CUDA_SUCCESS;
 }
 
 __global__ void clamp_count_kernel(const int64_t* raw, int64_t capacity, int64_t* out) {
@@ -709,6 +890,46 @@ __global__ void copy_back_kernel(const uint64_t* __restrict__ k, const uint32_t*
     }
 }
 
+template <typename CF>
+static int launch(const Params& Pin, bool allow_tma, cudaStream_t s) {
+    Params P = Pin;
+    P.tiles_x = (int)ceil_div(P.W, STRIP_W);            // strips
+    P.tiles_y = (int)ceil_div(P.rows_own, CF::TH);      // row blocks per strip
+    const long long total = (long long)P.tiles_x * P.tiles_y;
+    if (total == 0) return DM_OK;
+    // one persistent 16-warp CTA per SM; every warp takes one contiguous run of units
+    const long long max_warps = (long long)num_sms() * NWARPS;
+    const long long per = ceil_div(total, max_warps);
+    if (per > 0x7fffffff) return DM_ERR_BAD_ARG;
+    P.tiles_per_cta = (int)per;
+    const int grid = (int)ceil_div(ceil_div(total, per), NWARPS);
+
+    CUtensorMap mapL, mapI;
+    memset(&mapL, 0, sizeof(mapL));
+    memset(&mapI, 0, sizeof(mapI));
+    // TMA needs 16-byte aligned bases and row pitches; anything else takes the ld.global staging path
+    bool tma = allow_tma && ((uintptr_t)P.labels % 16 == 0) && ((P.ld * 4) % 16 == 0) && P.ld >= P.W;
+    if (CF::C > 0)
+        tma = tma && ((uintptr_t)P.image % 16 == 0) && (P.image_pitch % 16 == 0) && (((int64_t)P.W * CF::C) % 4 == 0);
+    if (tma)
+        tma = make_map_2d(&mapL, P.labels, (uint64_t)P.W, (uint64_t)P.rows_avail, (uint64_t)P.ld * 4, LAB_PITCH, CF::TH + 1);
+    if (tma && CF::C > 0)
+        tma = make_map_2d(&mapI, P.image, (uint64_t)P.W * CF::C / 4, (uint64_t)P.rows_own, (uint64_t)P.image_pitch,
+                          CF::IMG_ROW_WORDS, CF::TH);
+    g_last_path = tma ? 1 : 0;
+    if (tma) {
+        auto k = rag_pool_kernel<CF, true>;
+        DM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
+        DM_COUNT_LAUNCH(); k<<<grid, CF::THREADS, CF::SMEM_BYTES, s>>>(mapL, mapI, P);
+    } else {
+        auto k = rag_pool_kernel<CF, false>;
+        DM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
+        DM_COUNT_LAUNCH(); k<<<grid, CF::THREADS, CF::SMEM_BYTES, s>>>(mapL, mapI, P);
+    }
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
 // DM_RAG_NO_TMA=1 forces the ld.global staging path (tests exercise both).
 static bool allow_tma_env() {
     const char* e = getenv("DM_RAG_NO_TMA");
@@ -718,11 +939,11 @@ static bool allow_tma_env() {
 int run(const Params& P, int C, cudaStream_t s) {
     const bool tma = allow_tma_env();
     switch (C) {
-        case 0: return launch<Cfg<0, 32, 2, 4, 3>>(P, tma, s);
-        case 1: return launch<Cfg<1, 32, 2, 4, 3>>(P, tma, s);
-        case 2: return launch<Cfg<2, 32, 2, 4, 2>>(P, tma, s);
-        case 3: return launch<Cfg<3, 32, 2, 4, 2>>(P, tma, s);
-        case 4: return launch<Cfg<4, 32, 2, 4, 2>>(P, tma, s);
+        case 0: return launch<Cfg<0, 8, 2>>(P, tma, s);
+        case 1: return launch<Cfg<1, 4, 3>>(P, tma, s);
+        case 2: return launch<Cfg<2, 4, 2>>(P, tma, s);
+        case 3: return launch<Cfg<3, 4, 2>>(P, tma, s);
+        case 4: return launch<Cfg<4, 4, 2>>(P, tma, s);
         default: return DM_ERR_BAD_ARG;
     }
 }
@@ -731,6 +952,9 @@ int run(const Params& P, int C, cudaStream_t s) {
 }  // namespace dm
 
 using namespace dm;
+
+extern "C" int dm_rag_last_path(void) { return rag::last_path(); }
+extern "C" int dm_rag_last_encode_error(void) { return rag::last_encode_error(); }
 
 extern "C" size_t dm_rag_workspace_bytes(int64_t capacity) {
     const int64_t cap = capacity < 1 ? 1 : capacity;

@@ -106,6 +106,12 @@ int dm_rag_scan(const int32_t* labels, int64_t rows_own, int64_t rows_avail, int
 int dm_rag_finish(uint64_t* edge_keys, uint32_t* boundary_len, int64_t capacity, int64_t n_regions,
                   int64_t* counts, void* ws, size_t ws_bytes, dm_stream_t stream);
 
+/* Which staging path the last dm_rag_scan on this thread took: 1 = TMA (cp.async.bulk.tensor),
+ * 0 = ld.global (pitch / base not 16-byte aligned, or DM_RAG_NO_TMA=1), -1 = none yet; and the
+ * CUresult of the last cuTensorMapEncodeTiled (-1: driver entry point missing). */
+int dm_rag_last_path(void);
+int dm_rag_last_encode_error(void);
+
 /* Sort + unique (summing lengths) an arbitrary concatenation of (key,len) lists: used to
  * merge the per-tile lists of a sharded scene and inside the merge loop.  In place. */
 size_t dm_edges_unique_workspace_bytes(int64_t capacity);
