@@ -114,55 +114,50 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_hist(const uint64_t* __res
     hist[(size_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
 }
 
-// One block of 1024 threads = 256 digits x 4 tile quarters.  Turns per-tile digit counts
-// into global exclusive offsets (digit-major, then tile order) in place.
-__global__ void __launch_bounds__(1024) radix_offsets(uint32_t* __restrict__ hist, const int64_t* __restrict__ n_dev) {
+// One warp per digit (8 blocks x 32 warps): turns the per-tile counts of that digit into an
+// exclusive prefix over tiles (in place) and writes the digit's total to totals[d].  The
+// digit bases (exclusive scan of the 256 totals) are computed by every scatter block itself.
+__global__ void __launch_bounds__(1024) radix_offsets(uint32_t* __restrict__ hist, const int64_t* __restrict__ n_dev,
+                                                      uint32_t* __restrict__ totals) {
     const int64_t n = *n_dev;
     const int tiles = (int)((n + SORT_TILE - 1) / SORT_TILE);
-    const int d = threadIdx.x & 255, q = threadIdx.x >> 8;
-    const int per = (tiles + 3) / 4;
-    const int t0 = min(tiles, q * per), t1 = min(tiles, t0 + per);
-    __shared__ uint32_t qsum[4][256];
-    __shared__ uint32_t sm[1024 / 32 + 1];
-    uint32_t s = 0;
-    for (int t = t0; t < t1; ++t) s += hist[(size_t)t * 256 + d];
-    qsum[q][d] = s;
-    __syncthreads();
-    uint32_t dig_total = 0, total;
-    if (q == 0) dig_total = qsum[0][d] + qsum[1][d] + qsum[2][d] + qsum[3][d];
-    uint32_t dig_base = block_excl_scan<1024>(dig_total, sm, total);   // only q==0 lanes carry values
-    if (q == 0) {
-        uint32_t run = dig_base;
+    const int lane = threadIdx.x & 31;
+    const int d = blockIdx.x * 32 + (threadIdx.x >> 5);
+    uint32_t carry = 0;
+    for (int t0 = 0; t0 < tiles; t0 += 32) {
+        const int t = t0 + lane;
+        const uint32_t c = t < tiles ? hist[(size_t)t * 256 + d] : 0;
+        uint32_t inc = c;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t c = qsum[k][d];
-            qsum[k][d] = run;
-            run += c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
         }
+        if (t < tiles) hist[(size_t)t * 256 + d] = carry + inc - c;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    __syncthreads();
-    uint32_t run = qsum[q][d];
-    for (int t = t0; t < t1; ++t) {
-        size_t i = (size_t)t * 256 + d;
-        uint32_t c = hist[i];
-        hist[i] = run;
-        run += c;
-    }
+    if (lane == 0) totals[d] = carry;
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) radix_scatter(const uint64_t* __restrict__ kin,
                                                               const uint32_t* __restrict__ vin,
                                                               uint64_t* __restrict__ kout, uint32_t* __restrict__ vout,
                                                               const int64_t* __restrict__ n_dev, int id_bits, int shift,
-                                                              const uint32_t* __restrict__ hist) {
+                                                              const uint32_t* __restrict__ hist,
+                                                              const uint32_t* __restrict__ totals) {
     const int64_t n = *n_dev;
     const int64_t tile_base = (int64_t)blockIdx.x * SORT_TILE;
     if (tile_base >= n) return;
     constexpr int NW = SORT_THREADS / 32;
     __shared__ uint32_t wcnt[NW][256];
     __shared__ uint32_t goff[256];
+    __shared__ uint32_t sm_scan[SORT_THREADS / 32 + 1];
     for (int i = threadIdx.x; i < NW * 256; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
-    goff[threadIdx.x] = hist[(size_t)blockIdx.x * 256 + threadIdx.x];
+    {
+        uint32_t tot;
+        const uint32_t base = block_excl_scan<SORT_THREADS>(totals[threadIdx.x], sm_scan, tot);   // digit base
+        goff[threadIdx.x] = base + hist[(size_t)blockIdx.x * 256 + threadIdx.x];
+    }
     __syncthreads();
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t wbase = tile_base + (int64_t)warp * (32 * SORT_ITEMS);
@@ -230,6 +225,7 @@ size_t sort_ws_bytes(int64_t cap) {
     b += align_up((size_t)cap * sizeof(uint64_t), 256);
     b += align_up((size_t)cap * sizeof(uint32_t), 256);
     b += align_up((size_t)ceil_div(cap, SORT_TILE) * 256 * sizeof(uint32_t), 256);
+    b += align_up(256 * sizeof(uint32_t), 256);
     return b;
 }
 
@@ -241,14 +237,15 @@ int sort_pairs(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t cap
     uint64_t* k2 = c.take<uint64_t>(cap);
     uint32_t* v2 = c.take<uint32_t>(cap);
     uint32_t* hist = c.take<uint32_t>((size_t)ceil_div(cap, SORT_TILE) * 256);
+    uint32_t* totals = c.take<uint32_t>(256);
     const unsigned tiles = (unsigned)ceil_div(cap, SORT_TILE);
     const int passes = (key_bits + 7) / 8;
     uint64_t *ka = keys, *kb = k2;
     uint32_t *va = vals, *vb = vals ? v2 : nullptr;
     for (int p = 0; p < passes; ++p) {
         DM_COUNT_LAUNCH(); radix_hist<<<tiles, SORT_THREADS, 0, s>>>(ka, n_dev, id_bits, 8 * p, hist);
-        DM_COUNT_LAUNCH(); radix_offsets<<<1, 1024, 0, s>>>(hist, n_dev);
-        DM_COUNT_LAUNCH(); radix_scatter<<<tiles, SORT_THREADS, 0, s>>>(ka, va, kb, vb, n_dev, id_bits, 8 * p, hist);
+        DM_COUNT_LAUNCH(); radix_offsets<<<8, 1024, 0, s>>>(hist, n_dev, totals);
+        DM_COUNT_LAUNCH(); radix_scatter<<<tiles, SORT_THREADS, 0, s>>>(ka, va, kb, vb, n_dev, id_bits, 8 * p, hist, totals);
         uint64_t* tk = ka; ka = kb; kb = tk;
         uint32_t* tv = va; va = vb; vb = tv;
     }

@@ -151,6 +151,30 @@ struct Tables {
     unsigned long long* qekey;  // [EQ]
     unsigned* qecnt;            // [EQ]
     unsigned* qn;               // [0] region entries, [1] edge entries
+    unsigned* base;             // start of the warp's table arena (what the out-of-line slow paths rebuild from)
+
+    __device__ __forceinline__ static Tables from(unsigned* tab) {
+        Tables T;
+        T.base = tab;
+        T.rkey = (int*)tab;
+        T.rarea = tab + RS;
+        T.rborder = tab + 2 * RS;
+        T.rsum = tab + 3 * RS;
+        T.rsq = tab + (3 + C) * RS;
+        T.ekey = (unsigned long long*)(tab + (3 + 2 * C) * RS);
+        T.ecnt = tab + (3 + 2 * C) * RS + 2 * ES;
+        T.used = tab + (3 + 2 * C) * RS + 3 * ES;
+        unsigned* qb = T.used + 4;                                       // after used[2] + pad
+        T.qlabel = (int*)qb;
+        T.qarea = qb + RQ;
+        T.qborder = qb + 2 * RQ;
+        T.qsum = qb + 3 * RQ;
+        T.qsq = qb + (3 + C) * RQ;
+        T.qekey = (unsigned long long*)(qb + (3 + 2 * C) * RQ);
+        T.qecnt = qb + (3 + 2 * C) * RQ + 2 * EQ;
+        T.qn = qb + (3 + 2 * C) * RQ + 3 * EQ;
+        return T;
+    }
 };
 
 __device__ __forceinline__ int region_slot(int* rkey, unsigned* used, int label) {
@@ -269,6 +293,30 @@ __device__ __forceinline__ void table_region_add(const Tables<C>& T, const Param
     }
 }
 
+// Out-of-line slow paths (queue overflow, uncached border sides): kept out of the hot loop's code.
+template <int C>
+__device__ __noinline__ void slow_edge_add(unsigned* tab, const Params* P, unsigned long long key, unsigned cnt) {
+    edge_add<C>(Tables<C>::from(tab), *P, key, cnt);
+}
+template <int C>
+__device__ __noinline__ void slow_region_add(unsigned* tab, const Params* P, int label, unsigned area, unsigned border,
+                                             uint4 s4, uint4 q4) {
+    const unsigned s[4] = {s4.x, s4.y, s4.z, s4.w}, q[4] = {q4.x, q4.y, q4.z, q4.w};
+    table_region_add<C>(Tables<C>::from(tab), *P, label, area, border, s, q);
+}
+template <int C>
+__device__ __forceinline__ void slow_region_add_acc(const Tables<C>& T, const Params& P, int label, unsigned area,
+                                                    unsigned border, const unsigned* s, const unsigned* q) {
+    uint4 s4 = make_uint4(0, 0, 0, 0), q4 = make_uint4(0, 0, 0, 0);
+    if (C > 0 && s) {
+        s4.x = s[0]; q4.x = q[0];
+        if (C > 1) { s4.y = s[1 % (C > 0 ? C : 1)]; q4.y = q[1 % (C > 0 ? C : 1)]; }
+        if (C > 2) { s4.z = s[2 % (C > 0 ? C : 1)]; q4.z = q[2 % (C > 0 ? C : 1)]; }
+        if (C > 3) { s4.w = s[3 % (C > 0 ? C : 1)]; q4.w = q[3 % (C > 0 ? C : 1)]; }
+    }
+    slow_region_add<C>(T.base, &P, label, area, border, s4, q4);
+}
+
 // Evicted accumulators are only PUSHED by the (few, divergent) evicting lanes; the expensive
 // hash probe + atomics happen later in drain_queues with every queued entry on its own lane.
 template <int C>
@@ -285,7 +333,7 @@ __device__ __forceinline__ void acc_push(const Tables<C>& T, const Params& P, Ac
             T.qsq[c * RQ + p] = a.q[c];
         }
     } else {                      // queue full (it is drained every unit): rare, do it the slow way
-        table_region_add<C>(T, P, a.label, a.area, a.border, a.s, a.q);
+        slow_region_add_acc<C>(T, P, a.label, a.area, a.border, a.s, a.q);
     }
     a.clear();
 }
@@ -297,7 +345,7 @@ __device__ __forceinline__ void edge_push(const Tables<C>& T, const Params& P, u
         T.qekey[p] = key;
         T.qecnt[p] = cnt;
     } else {
-        edge_add<C>(T, P, key, cnt);
+        slow_edge_add<C>(T.base, &P, key, cnt);
     }
 }
 
@@ -412,7 +460,7 @@ struct Thread {
     __device__ __forceinline__ void border_add(const Tables<C>& T, const Params& P, int v, unsigned n) {
         if (v == c0.label) c0.border += n;
         else if (v == c1.label) c1.border += n;
-        else table_region_add<C>(T, P, v, 0, n, nullptr, nullptr);
+        else slow_region_add_acc<C>(T, P, v, 0, n, nullptr, nullptr);
     }
     // slow path: one pixel pair with different labels
     __device__ __forceinline__ void pair(const Tables<C>& T, const Params& P, int a, int b, unsigned n) {
@@ -429,6 +477,130 @@ struct Thread {
         }
     }
 };
+
+// One lane-row (4 pixels) of the walk.  SPECIAL = the unit touches an image border (first / last
+// strip, first / last rows): only then are pixels masked with `vm` and border sides counted.
+template <int C, bool SPECIAL>
+__device__ __forceinline__ void process_row(Thread<C>& th, int4& own, unsigned& m0, unsigned& m1, unsigned& use0,
+                                            unsigned& use1, const int4 dn, const int right, const unsigned* TB,
+                                            const Tables<C>& T, const Params& P, const unsigned vm, const bool left_edge,
+                                            const int last_k, const unsigned edge_rows, const int nin) {
+    const int4 a = own;
+    const bool any_neg = (a.x | a.y | a.z | a.w | right | dn.x | dn.y | dn.z | dn.w) < 0;
+    const unsigned negm = any_neg ? neg4(a) : 0u;
+    // masks of the lower row / right neighbour against the two cached labels (d* become the next row's m*)
+    unsigned d0 = match4(dn, th.c0.label), d1 = match4(dn, th.c1.label);
+    unsigned r0 = right == th.c0.label ? 0xff000000u : 0u, r1 = right == th.c1.label ? 0xff000000u : 0u;
+    unsigned xtra = 0;                 // own pixels accounted for without the cache (>2 labels in the lane)
+    if (((m0 | m1 | negm) & (d0 | d1 | (any_neg ? 0xffffffffu : 0u))) != 0xffffffffu || (!any_neg && !(r0 | r1))) {
+        // Some label around is not cached: load it.  One code instance serves the lane's own pixels,
+        // the right neighbour and the row below (the region that starts there is then already cached
+        // when the walk reaches it).  Entries (re)loaded in this row are pinned.
+        unsigned pinned = 0;
+#pragma unroll 1
+        for (int it = 0; it < 6; ++it) {
+            const unsigned c_own = m0 | m1 | negm | xtra;
+            int cand, i4 = 0;
+            bool for_own = false;
+            if (c_own != 0xffffffffu) {
+                i4 = (__ffs(~c_own) - 1) >> 3;
+                cand = pick4(a, i4);
+                for_own = true;
+            } else if (any_neg) {
+                break;                                    // nodata around: neighbours go through the slow path
+            } else if (!(r0 | r1)) {
+                cand = right;
+            } else if ((d0 | d1) != 0xffffffffu) {
+                cand = pick4(dn, (__ffs(~(d0 | d1)) - 1) >> 3);
+            } else {
+                break;
+            }
+            int which = -1;
+            if (th.c0.label < 0 && !(pinned & 1u)) which = 0;          // an empty entry first
+            else if (th.c1.label < 0 && !(pinned & 2u)) which = 1;
+            else if (m0 == 0 && !(pinned & 1u)) which = 0;             // else one this row's pixels do not use
+            else if (m1 == 0 && !(pinned & 2u)) which = 1;
+            if (which < 0) {
+                if (!for_own) break;                                   // three labels meet here: slow path below
+                STAT(1);
+                Acc<C> one;
+                one.reset(cand);
+                const unsigned bm = (0xffu << (8 * i4)) & vm;
+                acc_pixels<C>(one, bm, TB);
+                if (SPECIAL && bm)
+                    one.border = (left_edge && i4 == 0 ? 1u : 0u) + (i4 == last_k ? 1u : 0u) + edge_rows;
+                acc_push<C>(T, P, one);
+                xtra |= 0xffu << (8 * i4);
+                continue;
+            }
+            STAT(for_own ? 0 : 2);
+            th.evict(T, P, which, cand);
+            const unsigned mm = match4(a, cand), dd = match4(dn, cand), rr = right == cand ? 0xff000000u : 0u;
+            if (which == 0) { m0 = mm; d0 = dd; r0 = rr; pinned |= 1u; }
+            else            { m1 = mm; d1 = dd; r1 = rr; pinned |= 2u; }
+        }
+    }
+    if (any_neg) {                                     // cache labels are >= 0 or EMPTY(-1): keep nodata out
+        m0 &= ~negm;
+        m1 &= ~negm;
+    }
+    // ---- accumulate the 4 pixels ---------------------------------------------------------------------
+    {
+        const unsigned v0 = SPECIAL ? (m0 & vm) : m0, v1 = SPECIAL ? (m1 & vm) : m1;
+        acc_pixels<C>(th.c0, v0, TB);
+        acc_pixels<C>(th.c1, v1, TB);
+        if (SPECIAL) {
+            if (left_edge) {
+                th.c0.border += v0 & 1u;
+                th.c1.border += v1 & 1u;
+            }
+            if ((unsigned)last_k < 4u) {
+                th.c0.border += (v0 >> (8 * last_k)) & 1u;
+                th.c1.border += (v1 >> (8 * last_k)) & 1u;
+            }
+            if (edge_rows) {                            // warp-uniform: first / last raster row
+                th.c0.border += edge_rows * (__popc(v0) >> 3);
+                th.c1.border += edge_rows * (__popc(v1) >> 3);
+            }
+        }
+    }
+    // ---- neighbour pairs -----------------------------------------------------------------------------
+    use0 |= m0 | d0 | r0;
+    use1 |= m1 | d1 | r1;
+    if (!any_neg && ((m0 | m1) & (d0 | d1)) == 0xffffffffu && (r0 | r1)) {
+        // every label around is one of the two cached ones: pairs that straddle them are counted
+        // with byte-mask logic, no per-pair work and no divergence
+        const unsigned n0 = (m0 >> 8) | r0, n1 = (m1 >> 8) | r1;
+        const unsigned cross_h = (m0 & n1) | (m1 & n0);
+        unsigned cross_v = (m0 & d1) | (m1 & d0);
+        if (SPECIAL) cross_v &= vm;                     // padded copies right of the image do not pair
+        th.e01 += (__popc(cross_h) + __popc(cross_v)) >> 3;
+        STAT(3);
+    } else {
+        // a third label or nodata nearby: the 8 pairs one by one (bits 0-3 = (x,x+1), 4-7 = (y,y+1))
+        unsigned pm = (a.x != a.y ? 1u : 0u) | (a.y != a.z ? 2u : 0u) | (a.z != a.w ? 4u : 0u) |
+                      (a.w != right ? 8u : 0u) | (a.x != dn.x ? 16u : 0u) | (a.y != dn.y ? 32u : 0u) |
+                      (a.z != dn.z ? 64u : 0u) | (a.w != dn.w ? 128u : 0u);
+        if (SPECIAL) pm &= 0x0fu | (((1u << nin) - 1u) << 4);         // no vertical pairs right of the image
+        STAT(4);
+        while (pm) {
+            const int b = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const int k = b & 3;
+            const int pa = pick4(a, k);
+            const int pb = b < 4 ? (k == 0 ? a.y : k == 1 ? a.z : k == 2 ? a.w : right) : pick4(dn, k);
+            th.pair(T, P, pa, pb, 1);
+        }
+    }
+    own = dn;
+    m0 = d0;
+    m1 = d1;
+    if (any_neg) {                                     // EMPTY(-1) may have matched nodata pixels of the lower row
+        const unsigned nd = ~neg4(dn);
+        m0 &= nd;
+        m1 &= nd;
+    }
+}
 
 // Drain the warp's tables to global memory (whole warp, convergent).
 template <int C>
@@ -500,26 +672,7 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem + (size_t)warp * CF::WARP_BYTES;       // this warp's private arena
     unsigned* tab = (unsigned*)(wbase + NS * CF::STAGE_BYTES);
-    Tables<C> T;
-    T.rkey = (int*)tab;
-    T.rarea = tab + RS;
-    T.rborder = tab + 2 * RS;
-    T.rsum = tab + 3 * RS;
-    T.rsq = tab + (3 + C) * RS;
-    T.ekey = (unsigned long long*)(tab + (3 + 2 * C) * RS);
-    T.ecnt = tab + (3 + 2 * C) * RS + 2 * ES;
-    T.used = tab + (3 + 2 * C) * RS + 3 * ES;
-    {
-        unsigned* qb = T.used + 4;                                       // after used[2] + pad
-        T.qlabel = (int*)qb;
-        T.qarea = qb + RQ;
-        T.qborder = qb + 2 * RQ;
-        T.qsum = qb + 3 * RQ;
-        T.qsq = qb + (3 + C) * RQ;
-        T.qekey = (unsigned long long*)(qb + (3 + 2 * C) * RQ);
-        T.qecnt = qb + (3 + 2 * C) * RQ + 2 * EQ;
-        T.qn = qb + (3 + 2 * C) * RQ + 3 * EQ;
-    }
+    const Tables<C> T = Tables<C>::from(tab);
     uint64_t* full_bar = (uint64_t*)(tab + ((CF::TABLE_WORDS + 1) & ~1));
 
     // ---- this warp's run of units (unit = TH rows of one strip, column-major order) -------
@@ -574,9 +727,8 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     th.init();
     int units_since_drain = 0;
     int4 own = make_int4(0, 0, 0, 0);
-    unsigned m0 = 0, m1 = 0;
-    bool have_masks = false;            // m0/m1 valid for `own` against the current cache labels
-    bool use0 = false, use1 = false;    // cache entry touched during the current unit (see the GC below)
+    unsigned m0 = 0, m1 = 0;            // byte masks of `own` against the two cached labels
+    unsigned use0 = 0, use1 = 0;        // cache entry touched during the current unit (see the GC below)
     // (strip, row block) of the current unit, advanced incrementally (column-major order)
     int sx = (int)(u_begin / P.tiles_y), j = (int)(u_begin - (long long)sx * P.tiles_y);
     bool contiguous = false;
@@ -611,177 +763,88 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
         const int* L = Lw;
         const unsigned* I = (const unsigned*)(sb + CF::LAB_BOX);
         const int x0 = strip_x0 + 4 * lane;                 // first of this lane's 4 pixels
-        const int nin = min(4, max(0, P.W - x0));           // pixels of this lane inside the image
-        // Image borders without a separate code path: pixels right of the image are replaced by
-        // copies of the row's last pixel (so they never differ from a neighbour) and masked out of
-        // the accumulation with `vm`; border sides are added arithmetically below.
-        const unsigned vm = nin >= 4 ? 0xffffffffu : ((1u << (8 * nin)) - 1u);
-        const bool left_edge = (x0 == 0);
-        const int last_k = P.W - 1 - x0;                    // in [0,3] for the lane holding the last column
-        const int last_col = P.W - 1 - strip_x0;            // < STRIP_W only in the last strip
-        if (!contiguous) {                                  // new strip / first unit: nothing carried over
-            own = *(const int4*)(L + 4 * lane);
-            if (nin < 4) {
-                const int e = L[min(last_col, STRIP_W - 1)];
-                if (nin < 1) own.x = e;
-                if (nin < 2) own.y = e;
-                if (nin < 3) own.z = e;
-                own.w = e;
+        // a unit is "special" when it touches an image border: only those pay for border logic
+        const bool special = (sx == 0) || (sx == P.tiles_x - 1) || (unit_y0 == 0) || (unit_y0 + TH >= P.rows_own);
+        if (!special) {
+            if (!contiguous) {
+                own = *(const int4*)(L + 4 * lane);
+                m0 = match4(own, th.c0.label);
+                m1 = match4(own, th.c1.label);
             }
-            have_masks = false;
-        }
 #pragma unroll 1
-        for (int r = 0; r < TH; ++r) {
-            const int y = unit_y0 + r;
-            if (y >= P.rows_own) break;
-            const bool has_dn = (y + 1 < P.rows_avail);     // warp-uniform
-            int4 dn = *(const int4*)(L + (r + 1) * LAB_PITCH + 4 * lane);
-            int right = __shfl_down_sync(0xffffffffu, own.x, 1);
-            if (lane == 31) right = L[r * LAB_PITCH + STRIP_W];
-            if (nin < 4) {                                  // only lanes of the last strip
-                const int e = L[(r + 1) * LAB_PITCH + min(last_col, STRIP_W - 1)];
-                if (nin < 1) dn.x = e;
-                if (nin < 2) dn.y = e;
-                if (nin < 3) dn.z = e;
-                dn.w = e;
-            }
-            if (!has_dn) dn = own;                          // last raster row: no vertical pairs
-            if (x0 + 4 >= P.W) right = own.w;               // nothing to the right of the last column
-            unsigned W[CF::CW], TB[CF::CW];
-            if (C > 0) {
-                if (C == 4) {
-                    const uint4 v = *(const uint4*)(I + r * CF::IMG_ROW_WORDS + 4 * lane);
-                    W[0] = v.x; W[1 % CF::CW] = v.y; W[2 % CF::CW] = v.z; W[3 % CF::CW] = v.w;
-                } else {
+            for (int r = 0; r < TH; ++r) {
+                const int4 dn = *(const int4*)(L + (r + 1) * LAB_PITCH + 4 * lane);
+                int right = __shfl_down_sync(0xffffffffu, own.x, 1);
+                if (lane == 31) right = L[r * LAB_PITCH + STRIP_W];
+                unsigned W[CF::CW], TB[CF::CW];
+                if (C > 0) {
+                    if (C == 4) {
+                        const uint4 v = *(const uint4*)(I + r * CF::IMG_ROW_WORDS + 4 * lane);
+                        W[0] = v.x; W[1 % CF::CW] = v.y; W[2 % CF::CW] = v.z; W[3 % CF::CW] = v.w;
+                    } else {
 #pragma unroll
-                    for (int c = 0; c < C; ++c) W[c] = I[r * CF::IMG_ROW_WORDS + C * lane + c];
+                        for (int c = 0; c < C; ++c) W[c] = I[r * CF::IMG_ROW_WORDS + C * lane + c];
+                    }
+                    band_transpose<C>(W, TB);
                 }
-                band_transpose<C>(W, TB);
+                process_row<C, false>(th, own, m0, m1, use0, use1, dn, right, TB, T, P, 0xffffffffu, false, -1, 0u, 4);
             }
-            const int4 a = own;
-            // ---- the 4 pixels go into the 2-entry label cache ------------------------------
-            if (!have_masks) {
-                m0 = match4(a, th.c0.label);
-                m1 = match4(a, th.c1.label);
-            }
-            const bool any_neg = (a.x | a.y | a.z | a.w | right | dn.x | dn.y | dn.z | dn.w) < 0;
-            unsigned covered = m0 | m1;
-            if (any_neg) covered |= neg4(a);
-            // side counts of this row that face the image border (left / right column, first / last row)
-            const bool top_row = (y == 0) && P.top_border;
-            const bool bot_row = (!has_dn) && (y == P.rows_own - 1) && P.bottom_border;
-            while (covered != 0xffffffffu) {               // a label outside the cache
-                const int i4 = (__ffs(~covered) - 1) >> 3;
-                const int Lb = pick4(a, i4);
-                if (m0 == 0 || th.c0.label < 0) {
-                    STAT(0);
-                    STAT_LAST(Lb, 10);
-                    th.evict(T, P, 0, Lb);
-                    m0 = match4(a, Lb);
-                    covered |= m0;
-                } else if (m1 == 0 || th.c1.label < 0) {
-                    STAT(0);
-                    STAT_LAST(Lb, 10);
-                    th.evict(T, P, 1, Lb);
-                    m1 = match4(a, Lb);
-                    covered |= m1;
-                } else {                                   // >2 labels in 4 pixels: uncached add
-                    STAT(1);
-                    Acc<C> one;
-                    one.reset(Lb);
-                    const unsigned bm = (0xffu << (8 * i4)) & vm;
-                    acc_pixels<C>(one, bm, TB);
-                    if (bm) one.border = (left_edge && i4 == 0 ? 1u : 0u) + (i4 == last_k ? 1u : 0u) + (top_row ? 1u : 0u) +
-                                         (bot_row ? 1u : 0u);
-                    acc_push<C>(T, P, one);
-                    covered |= 0xffu << (8 * i4);
+        } else {
+            // Image borders without a separate per-pixel path: pixels right of the image are replaced
+            // by copies of the row's last pixel (so they never differ from a neighbour) and masked out
+            // of the accumulation with `vm`; border sides are added arithmetically.
+            const int nin = min(4, max(0, P.W - x0));       // pixels of this lane inside the image
+            const unsigned vm = nin >= 4 ? 0xffffffffu : ((1u << (8 * nin)) - 1u);
+            const bool left_edge = (x0 == 0);
+            const int last_k = P.W - 1 - x0;                // in [0,3] for the lane holding the last column
+            const int last_col = min(P.W - 1 - strip_x0, STRIP_W - 1);
+            if (!contiguous) {
+                own = *(const int4*)(L + 4 * lane);
+                if (nin < 4) {
+                    const int e = L[last_col];
+                    if (nin < 1) own.x = e;
+                    if (nin < 2) own.y = e;
+                    if (nin < 3) own.z = e;
+                    own.w = e;
                 }
+                m0 = match4(own, th.c0.label);
+                m1 = match4(own, th.c1.label);
+                const unsigned nd = ~neg4(own);
+                m0 &= nd;
+                m1 &= nd;
             }
-            if (any_neg) {                                 // cache labels are >= 0 or EMPTY(-1): keep nodata out
-                const unsigned ok = ~neg4(a);
-                m0 &= ok;
-                m1 &= ok;
-            }
-            {
-                const unsigned v0 = m0 & vm, v1 = m1 & vm;
-                acc_pixels<C>(th.c0, v0, TB);
-                acc_pixels<C>(th.c1, v1, TB);
-                if (left_edge) {
-                    th.c0.border += v0 & 1u;
-                    th.c1.border += v1 & 1u;
-                }
-                if ((unsigned)last_k < 4u) {
-                    th.c0.border += (v0 >> (8 * last_k)) & 1u;
-                    th.c1.border += (v1 >> (8 * last_k)) & 1u;
-                }
-                if (top_row | bot_row) {                    // warp-uniform
-                    const unsigned n = (top_row ? 1u : 0u) + (bot_row ? 1u : 0u);
-                    th.c0.border += n * (__popc(v0) >> 3);
-                    th.c1.border += n * (__popc(v1) >> 3);
-                }
-            }
-            // ---- neighbour pairs -------------------------------------------------------------
-            // masks of the lower row against the same two labels: reused as the next row's m0/m1
-            unsigned d0 = match4(dn, th.c0.label), d1 = match4(dn, th.c1.label);
-            bool r0m = right == th.c0.label, r1m = right == th.c1.label;
-            const bool own_ok = !any_neg && ((m0 | m1) == 0xffffffffu);   // 4 pixels fully cached, no nodata around
-            bool nbr_ok = ((d0 | d1) == 0xffffffffu) && (r0m | r1m);
-            if (own_ok && !nbr_ok) {
-                // a neighbour label that is not cached (a boundary running along this lane's edge,
-                // or the region that starts in the next row): bring it into a cache entry none of
-                // this row's pixels use, so that the row still takes the convergent path below
 #pragma unroll 1
-                for (int tries = 0; tries < 2; ++tries) {
-                    const unsigned dcov = d0 | d1;
-                    int cand;
-                    if (!(r0m | r1m)) cand = right;
-                    else if (dcov != 0xffffffffu) cand = pick4(dn, (__ffs(~dcov) - 1) >> 3);
-                    else break;
-                    if (m0 == 0) th.evict(T, P, 0, cand);
-                    else if (m1 == 0) th.evict(T, P, 1, cand);
-                    else break;                            // three labels meet here: slow path
-                    STAT(2);
-                    if (cand == right) STAT(7);
-                    if (tries == 1) STAT(8);
-                    STAT_LAST(cand, 9);
-                    d0 = match4(dn, th.c0.label);
-                    d1 = match4(dn, th.c1.label);
-                    r0m = right == th.c0.label;
-                    r1m = right == th.c1.label;
+            for (int r = 0; r < TH; ++r) {
+                const int y = unit_y0 + r;
+                if (y >= P.rows_own) break;
+                const bool has_dn = (y + 1 < P.rows_avail);     // warp-uniform
+                int4 dn = *(const int4*)(L + (r + 1) * LAB_PITCH + 4 * lane);
+                int right = __shfl_down_sync(0xffffffffu, own.x, 1);
+                if (lane == 31) right = L[r * LAB_PITCH + STRIP_W];
+                if (nin < 4) {                                  // only lanes of the last strip
+                    const int e = L[(r + 1) * LAB_PITCH + last_col];
+                    if (nin < 1) dn.x = e;
+                    if (nin < 2) dn.y = e;
+                    if (nin < 3) dn.z = e;
+                    dn.w = e;
                 }
-                nbr_ok = ((d0 | d1) == 0xffffffffu) && (r0m | r1m);
-            }
-            use0 |= (m0 | d0) != 0 || r0m;
-            use1 |= (m1 | d1) != 0 || r1m;
-            if (own_ok && nbr_ok) {
-                // every label around is one of the two cached ones: pairs that straddle them are
-                // counted with byte-mask logic, no per-pair work and no divergence
-                const unsigned n0 = (m0 >> 8) | (r0m ? 0xff000000u : 0u);
-                const unsigned n1 = (m1 >> 8) | (r1m ? 0xff000000u : 0u);
-                const unsigned cross_h = (m0 & n1) | (m1 & n0);
-                const unsigned cross_v = ((m0 & d1) | (m1 & d0)) & vm;      // padded copies right of the image do not pair
-                th.e01 += (__popc(cross_h) + __popc(cross_v)) >> 3;
-                STAT(3);
-            } else {
-                // a third label or nodata nearby: the 8 pairs one by one (bits 0-3 = (x,x+1), 4-7 = (y,y+1))
-                unsigned pm = (a.x != a.y ? 1u : 0u) | (a.y != a.z ? 2u : 0u) | (a.z != a.w ? 4u : 0u) |
-                              (a.w != right ? 8u : 0u) | (a.x != dn.x ? 16u : 0u) | (a.y != dn.y ? 32u : 0u) |
-                              (a.z != dn.z ? 64u : 0u) | (a.w != dn.w ? 128u : 0u);
-                pm &= 0x0fu | (((1u << nin) - 1u) << 4);                    // no vertical pairs right of the image
-                STAT(4);
-                while (pm) {
-                    const int b = __ffs(pm) - 1;
-                    pm &= pm - 1;
-                    const int k = b & 3;
-                    const int pa = pick4(a, k);
-                    const int pb = b < 4 ? (k == 0 ? a.y : k == 1 ? a.z : k == 2 ? a.w : right) : pick4(dn, k);
-                    th.pair(T, P, pa, pb, 1);
+                if (!has_dn) dn = own;                          // last raster row: no vertical pairs
+                if (x0 + 4 >= P.W) right = own.w;               // nothing to the right of the last column
+                unsigned W[CF::CW], TB[CF::CW];
+                if (C > 0) {
+                    if (C == 4) {
+                        const uint4 v = *(const uint4*)(I + r * CF::IMG_ROW_WORDS + 4 * lane);
+                        W[0] = v.x; W[1 % CF::CW] = v.y; W[2 % CF::CW] = v.z; W[3 % CF::CW] = v.w;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) W[c] = I[r * CF::IMG_ROW_WORDS + C * lane + c];
+                    }
+                    band_transpose<C>(W, TB);
                 }
+                const unsigned edge_rows = ((y == 0 && P.top_border) ? 1u : 0u) +
+                                           ((!has_dn && y == P.rows_own - 1 && P.bottom_border) ? 1u : 0u);
+                process_row<C, true>(th, own, m0, m1, use0, use1, dn, right, TB, T, P, vm, left_edge, last_k, edge_rows, nin);
             }
-            own = dn;
-            m0 = d0;
-            m1 = d1;
-            have_masks = !any_neg;
         }
 
         // ---- convergent garbage collection of the label cache --------------------------------------
@@ -798,7 +861,7 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
                 th.c1.label = EMPTY_LABEL;
             }
         }
-        use0 = use1 = false;
+        use0 = use1 = 0;
         // next unit of this warp's run
         contiguous = (j + 1 < P.tiles_y);
         if (contiguous) ++j;

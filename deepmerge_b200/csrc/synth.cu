@@ -109,13 +109,14 @@ __global__ void points_kernel(int32_t* __restrict__ xs, int32_t* __restrict__ ys
 }
 
 __global__ void feats_kernel(float* __restrict__ feats, const int32_t* __restrict__ rop, const int32_t* __restrict__ region_obj,
-                             int64_t n, int D, uint32_t seed) {
+                             const int64_t* __restrict__ point_ids, int64_t n, int D, uint32_t seed) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * D; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p = i / D;
         const int d = (int)(i - p * D);
         const int r = rop[p];
         const int obj = r >= 0 ? region_obj[r] : 0;
-        const uint32_t hc = hash32(seed + 6, obj, d), hn = hash32(seed + 7, (uint32_t)p, d);
+        const uint32_t gid = (uint32_t)(point_ids ? point_ids[p] : p);   // global point id: the scene does not depend on sharding
+        const uint32_t hc = hash32(seed + 6, obj, d), hn = hash32(seed + 7, gid, d);
         const int ci = (int)(hc & 0xffff) + (int)(hc >> 16) - 65535;
         const int ni = (int)(hn & 0xffff) + (int)(hn >> 16) - 65535;
         feats[i] = (float)(ci * 128 + ni) * (1.0f / 2097152.0f);
@@ -166,12 +167,12 @@ extern "C" int dm_synth_points(int32_t* xs, int32_t* ys, int64_t H, int64_t W, i
     return DM_OK;
 }
 
-extern "C" int dm_synth_feats(float* feats, const int32_t* rop, const int32_t* region_obj, int64_t n, int64_t D, uint32_t seed,
-                              dm_stream_t stream) {
+extern "C" int dm_synth_feats(float* feats, const int32_t* rop, const int32_t* region_obj, const int64_t* point_ids,
+                              int64_t n, int64_t D, uint32_t seed, dm_stream_t stream) {
     if (n < 0 || D <= 0) return DM_ERR_BAD_ARG;
     if (n == 0) return DM_OK;
     if (!feats || !rop || !region_obj) return DM_ERR_BAD_ARG;
-    DM_COUNT_LAUNCH(); synth::feats_kernel<<<synth::grid_for(n * D), 256, 0, S(stream)>>>(feats, rop, region_obj, n, (int)D, seed);
+    DM_COUNT_LAUNCH(); synth::feats_kernel<<<synth::grid_for(n * D), 256, 0, S(stream)>>>(feats, rop, region_obj, point_ids, n, (int)D, seed);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

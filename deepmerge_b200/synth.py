@@ -55,5 +55,5 @@ def synth_scene(H, W, R, C=4, P=4, D=100, seed=1234, device=None, rows=None, wit
         if rows is None:
             rop = points_region(labels, xs, ys)
             feats = torch.empty((nreg * P, D), dtype=torch.float32, device=dev)
-            L.check(L.dm_synth_feats(_p(feats), _p(rop), _p(robj), nreg * P, D, seed, s), "dm_synth_feats")
+            L.check(L.dm_synth_feats(_p(feats), _p(rop), _p(robj), None, nreg * P, D, seed, s), "dm_synth_feats")
     return Scene(labels, image, xs, ys, rop, feats, robj, nreg, H, W)

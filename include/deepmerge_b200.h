@@ -245,8 +245,9 @@ int dm_synth_image(uint8_t* image, const int32_t* labels, int64_t y0, int64_t ro
                    int64_t C, const int32_t* region_obj, uint32_t seed, dm_stream_t stream);
 int dm_synth_points(int32_t* xs, int32_t* ys, int64_t H, int64_t W, int64_t pitch_g, int64_t P, uint32_t seed,
                     dm_stream_t stream);
-int dm_synth_feats(float* feats, const int32_t* region_of_point, const int32_t* region_obj, int64_t n_points,
-                   int64_t D, uint32_t seed, dm_stream_t stream);
+/* point_ids (nullable): global ids of the n_points rows (a row-tile shard passes the ids of its own points) */
+int dm_synth_feats(float* feats, const int32_t* region_of_point, const int32_t* region_obj, const int64_t* point_ids,
+                   int64_t n_points, int64_t D, uint32_t seed, dm_stream_t stream);
 
 #ifdef __cplusplus
 }

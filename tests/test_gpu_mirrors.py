@@ -1,0 +1,74 @@
+"""GPU: the reference-named callables against golden vectors produced by executing the reference."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as o
+
+pytestmark = pytest.mark.gpu
+
+
+def test_euclidean_distance_drop_in(cuda, golden_dir):
+    from deepmerge_b200.ExtractFeatures import Euclidean_distance, MC_Lyu_2020
+    e = np.load(os.path.join(golden_dir, "euclid.npz"))
+    D = Euclidean_distance(e["Xm"], e["Ym"])
+    assert D.dtype == np.float32 and D.shape == e["Dm"].shape
+    np.testing.assert_allclose(D, e["Dm"], rtol=1e-3)                       # north-star tolerance for fp32 scores
+    assert np.array_equal(MC_Lyu_2020(e["Xm"], e["Ym"]), D)
+    K = e["X"].shape[0]
+    d = np.array([Euclidean_distance(e["X"][i:i + 1], e["Y"][i:i + 1])[0, 0] for i in range(0, K, 7)])
+    mean = np.concatenate([e["X"], e["Y"]])
+    keys = o.pack_keys(np.arange(0, K, 7), np.arange(0, K, 7) + K)
+    assert np.all(np.abs(d - o.score_l2_f64(mean, keys)) <= o.l2_abs_tolerance(mean, keys))
+    with pytest.raises(ValueError):
+        Euclidean_distance(np.zeros((2, 3)), np.zeros((2, 4)))
+
+
+def test_pool_and_score_matches_reference_loop(cuda, golden_dir):
+    from deepmerge_b200.ExtractFeatures import pool_and_score
+    p = np.load(os.path.join(golden_dir, "pool_score.npz"))
+    means, simi = pool_and_score(p["store"], list(p["fields"]), p["left"], p["right"])
+    u = p["used"]
+    assert np.array_equal(means[u], p["means"][u])                          # np.mean(axis=0), bit exact
+    assert simi.dtype == np.float64
+    np.testing.assert_allclose(simi, p["simi"], rtol=1e-3)
+
+
+def test_loss_forward_backward_matches_reference(cuda, golden_dir):
+    import torch
+    from deepmerge_b200.Losses import Loss
+    l = np.load(os.path.join(golden_dir, "loss.npz"))
+    for mg in (1.0, 2.5):
+        a = torch.from_numpy(l["a"]).to(cuda).requires_grad_(True)
+        b = torch.from_numpy(l["b"]).to(cuda).requires_grad_(True)
+        loss = Loss(mg, 0.1, 0)(a, b, torch.from_numpy(l["flag"]).to(cuda))
+        (3.0 * loss).backward()                                             # upstream gradient is honoured
+        np.testing.assert_allclose(loss.item(), l[f"loss_{mg}"], rtol=1e-5)
+        np.testing.assert_allclose(a.grad.cpu().numpy(), 3.0 * l[f"ga_{mg}"], rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(b.grad.cpu().numpy(), 3.0 * l[f"gb_{mg}"], rtol=1e-5, atol=1e-8)
+    with pytest.raises(ValueError):
+        Loss(1.0, 0.1, 0)(torch.zeros(2, 3), torch.zeros(2, 3), torch.zeros(2))
+
+
+def test_pair_training_step_gather_plus_loss(cuda):
+    """R10 + R11 together: sampled point pairs -> gathered embedding rows -> loss + grads."""
+    import torch
+    from deepmerge_b200._lib import lib
+    from deepmerge_b200.Losses import Loss
+    rng = np.random.default_rng(3)
+    table = rng.standard_normal((500, 100)).astype(np.float32)
+    left, right = rng.integers(0, 500, 960), rng.integers(0, 500, 960)
+    flag = rng.integers(0, 2, 960)
+    L = lib()
+    t = torch.from_numpy(table).to(cuda)
+    ga = torch.empty((960, 100), device=cuda)
+    gb = torch.empty((960, 100), device=cuda)
+    L.check(L.dm_gather_rows(t.data_ptr(), 100, torch.from_numpy(left).to(cuda).data_ptr(), 960, ga.data_ptr(), None), "g")
+    L.check(L.dm_gather_rows(t.data_ptr(), 100, torch.from_numpy(right).to(cuda).data_ptr(), 960, gb.data_ptr(), None), "g")
+    assert np.array_equal(ga.cpu().numpy(), table[left]) and np.array_equal(gb.cpu().numpy(), table[right])
+    loss = Loss(1.0, 0.1, 0)(ga.requires_grad_(True), gb, torch.from_numpy(flag).to(cuda))
+    want, wga, _ = o.contrastive_loss(table[left], table[right], flag, 1.0)
+    np.testing.assert_allclose(loss.item(), want, rtol=1e-5)
+    loss.backward()
+    np.testing.assert_allclose(ga.grad.cpu().numpy(), wga, rtol=1e-4, atol=1e-8)

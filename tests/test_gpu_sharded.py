@@ -1,0 +1,99 @@
+"""GPU: the sharded engine with 2 and 3 virtual ranks emulated as THREADS of one process on one GPU
+(a fake torch.distributed whose collectives meet on host barriers; no kernel ever waits on another
+kernel), compared with the single-GPU engine and with the oracle."""
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as o
+
+pytestmark = pytest.mark.gpu
+
+
+class FakeDist:
+    """Minimal torch.distributed look-alike for `world` threads in one process."""
+
+    class ReduceOp:
+        SUM, MAX = "sum", "max"
+
+    def __init__(self, world):
+        import torch
+        self.world, self.torch = world, torch
+        self.bar = threading.Barrier(world)
+        self.slots = [None] * world
+        self.local = threading.local()
+
+    def get_world_size(self, group=None):
+        return self.world
+
+    def get_rank(self, group=None):
+        return self.local.rank
+
+    def _exchange(self, t):
+        self.torch.cuda.synchronize()
+        self.slots[self.local.rank] = t.clone()
+        self.bar.wait()
+        vals = [s.clone() for s in self.slots]
+        self.bar.wait()
+        return vals
+
+    def all_gather(self, out_list, t, group=None):
+        for dst, src in zip(out_list, self._exchange(t)):
+            dst.copy_(src)
+
+    def all_reduce(self, t, op="sum", group=None):
+        vals = self._exchange(t)
+        acc = vals[0].clone()
+        for v in vals[1:]:                      # fixed rank order
+            acc = acc + v if op == "sum" else self.torch.maximum(acc, v)
+        t.copy_(acc)
+
+
+@pytest.mark.parametrize("world,H,W,R", [(2, 260, 384, 500), (3, 301, 640, 1500)])
+def test_sharded_equals_single_gpu_and_oracle(cuda, world, H, W, R):
+    import torch
+    from deepmerge_b200 import merge_scene
+    from deepmerge_b200.sharded import ShardedMergeEngine, points_in_tile, tile_bounds
+    sc = o.synth_scene(H, W, R, C=4)
+    n, D = sc["n_regions"], sc["feats"].shape[1]
+    want = o.merge_scene(sc["labels"], n, sc["region_of_point"], sc["feats"], tau=0.5)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    fd = FakeDist(world)
+    results, errors = [None] * world, []
+
+    def rank_main(rank):
+        try:
+            fd.local.rank = rank
+            torch.cuda.set_device(cuda)
+            y0, y1 = tile_bounds(H, world, rank)
+            last = rank == world - 1
+            labels = T(sc["labels"][y0:y1 + (0 if last else 1)])
+            image = T(sc["image"][y0:y1])
+            mine = points_in_tile(torch.from_numpy(sc["ys"]), y0, y1).numpy()
+            eng = ShardedMergeEngine(H, W, n, D, 4, len(mine), fd, cuda)
+            res = eng.run(labels, T(sc["feats"][mine]), 0.5, image_tile=image, xs_local=T(sc["xs"][mine]),
+                          ys_local_rel=T(sc["ys"][mine] - y0))
+            torch.cuda.synchronize()
+            results[rank] = (res.labels.cpu().numpy(), res.root.cpu().numpy(), res.rounds, res.merges,
+                             res.area.cpu().numpy(), res.perimeter.cpu().numpy(),
+                             res.edge_keys.cpu().numpy().view(np.uint64), eng.eng.bsum.cpu().numpy().view(np.uint64))
+        except Exception as e:          # surface thread failures in the test
+            errors.append(e)
+            fd.bar.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    full = np.concatenate([r[0] for r in results])
+    assert np.array_equal(full, want["labels"])                       # final label map bit exact
+    roots = np.unique(want["root"])
+    s, _ = o.pool_bands(sc["labels"], sc["image"], n)
+    for r in results:
+        assert np.array_equal(r[1], want["root"]) and r[2] == want["rounds"] and r[3] == want["merges"]
+        assert np.array_equal(r[4][roots], want["area"][roots]) and np.array_equal(r[5][roots], want["perim"][roots])
+        assert np.array_equal(r[6], want["keys"])
+        assert np.array_equal(r[7], s)                                # band sums: integer all-reduce, exact
+    single = merge_scene(T(sc["labels"]), T(sc["feats"]), 0.5, n_regions=n, image=T(sc["image"]), xs=T(sc["xs"]), ys=T(sc["ys"]))
+    assert np.array_equal(single.labels.cpu().numpy(), full)
