@@ -40,16 +40,6 @@ constexpr int EMPTY_LABEL = -1;
 constexpr unsigned long long EMPTY_KEY = ~0ull;
 constexpr int SLOT_UNKNOWN = -2, SLOT_NONE = -1;
 
-#if defined(DM_RAG_STATS) && !defined(DM_RAG_TIMING_ONLY)
-#define STAT(i) atomicAdd(&P.counters[8 + (i)], 1ull)   // counts[] must hold >= 24 entries in a stats build
-#define STAT_LAST(l, i) do { if ((l) == th.last_evicted) STAT(i); } while (0)
-#else
-#define STAT(i) ((void)0)
-#define STAT_LAST(l, i) ((void)0)
-#endif
-// stats: 7 prefetch for right, 8 second prefetch in a row, 9/10 prefetch/own-miss of the label evicted last
-// stats: 0 own-miss evict, 1 uncached add, 2 prefetch evict, 3 fast lane-rows, 4 slow lane-rows, 5 border lane-rows, 6 drains
-
 constexpr int align128(int x) { return (x + 127) / 128 * 128; }
 
 template <int C_, int TH_, int NS_>
@@ -387,7 +377,15 @@ __device__ __forceinline__ unsigned neg4(const int4& a) {
     m |= (a.w < 0) ? 0xff000000u : 0u;
     return m;
 }
-__device__ __forceinline__ int pick4(const int4& a, int i) { return i == 0 ? a.x : i == 1 ? a.y : i == 2 ? a.z : a.w; }
+// branch-free select (the compiler turns ?: chains on a runtime index into divergent branches)
+__device__ __forceinline__ int selp(int a, int b, bool p) {
+    int r;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tselp.s32 %0, %1, %2, q;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((int)p));
+    return r;
+}
+__device__ __forceinline__ int pick4(const int4& a, int i) {
+    return selp(selp(a.x, a.y, i == 0), selp(a.z, a.w, i == 2), i < 2);
+}
 
 template <int C>
 __device__ __forceinline__ void acc_pixels(Acc<C>& a, unsigned bm, const unsigned* T) {
@@ -414,18 +412,13 @@ __device__ __forceinline__ void band_transpose(const unsigned* W, unsigned* T) {
 
 template <int C>
 struct Thread {
-    Acc<C> c0, c1;              // 2-entry label cache with per-label accumulators
-    unsigned e01;               // pixel pairs seen between c0.label and c1.label (fast path)
-    unsigned long long ekey;    // 1-entry run cache of the slow path
-    unsigned ecnt;
-#if defined(DM_RAG_STATS) && !defined(DM_RAG_TIMING_ONLY)
-    int last_evicted = -7;
-#endif
+    Acc<C> c0, c1;              // 2-entry label cache with per-label accumulators (own-row pixels only)
+    unsigned long long ekey;    // 1-entry run cache of the pair counter: a boundary that runs down
+    unsigned ecnt;              // through this lane's column produces the same key row after row
 
     __device__ __forceinline__ void init() {
         c0.reset(EMPTY_LABEL);
         c1.reset(EMPTY_LABEL);
-        e01 = 0;
         ekey = EMPTY_KEY;
         ecnt = 0;
     }
@@ -433,26 +426,7 @@ struct Thread {
         if (ecnt) edge_push<C>(T, P, ekey, ecnt);
         ecnt = 0;
     }
-    __device__ __forceinline__ void e01_flush(const Tables<C>& T, const Params& P) {
-        if (e01) edge_push<C>(T, P, pack_key(c0.label, c1.label), e01);
-        e01 = 0;
-    }
-    // replace cache entry `which` (0/1) by label l
-    __device__ __forceinline__ void evict(const Tables<C>& T, const Params& P, int which, int l) {
-#if defined(DM_RAG_STATS) && !defined(DM_RAG_TIMING_ONLY)
-        last_evicted = which == 0 ? c0.label : c1.label;
-#endif
-        e01_flush(T, P);
-        if (which == 0) {
-            acc_push<C>(T, P, c0);
-            c0.label = l;
-        } else {
-            acc_push<C>(T, P, c1);
-            c1.label = l;
-        }
-    }
     __device__ __forceinline__ void flush_all(const Tables<C>& T, const Params& P) {
-        e01_flush(T, P);
         acc_push<C>(T, P, c0);
         acc_push<C>(T, P, c1);
         edge_flush(T, P);
@@ -462,7 +436,7 @@ struct Thread {
         else if (v == c1.label) c1.border += n;
         else slow_region_add_acc<C>(T, P, v, 0, n, nullptr, nullptr);
     }
-    // slow path: one pixel pair with different labels
+    // n pixel pairs between labels a and b (a != b)
     __device__ __forceinline__ void pair(const Tables<C>& T, const Params& P, int a, int b, unsigned n) {
         if ((a | b) >= 0) {
             const unsigned long long k = pack_key(a, b);
@@ -478,128 +452,100 @@ struct Thread {
     }
 };
 
-// One lane-row (4 pixels) of the walk.  SPECIAL = the unit touches an image border (first / last
-// strip, first / last rows): only then are pixels masked with `vm` and border sides counted.
+// image-border sides of the pixels in byte mask v (border units only)
+__device__ __forceinline__ unsigned border_sides(unsigned v, bool left_edge, int last_k, unsigned edge_rows) {
+    unsigned n = edge_rows * (__popc(v) >> 3);
+    if (left_edge) n += v & 1u;
+    if ((unsigned)last_k < 4u) n += (v >> (8 * last_k)) & 1u;
+    return n;
+}
+
+// One lane-row (4 pixels) of the walk.  Two independent parts:
+//   statistics  the 4 own pixels are accumulated into the two cached labels with byte masks
+//               (no divergence while the lane sees at most two labels); a label that is not
+//               cached replaces an entry this row does not use (its accumulators are pushed to
+//               the warp's eviction queue), a third label inside the 4 pixels is pushed directly;
+//   pairs       the 8 neighbour pairs this lane owns ((x,x+1) and (y,y+1) of its 4 pixels) are
+//               compared; differing ones go one by one through the lane's run cache.
+// SPECIAL = the unit touches an image border: pixels (and vertical pairs) are masked with `vm` and
+// border sides are counted.
 template <int C, bool SPECIAL>
-__device__ __forceinline__ void process_row(Thread<C>& th, int4& own, unsigned& m0, unsigned& m1, unsigned& use0,
-                                            unsigned& use1, const int4 dn, const int right, const unsigned* TB,
-                                            const Tables<C>& T, const Params& P, const unsigned vm, const bool left_edge,
-                                            const int last_k, const unsigned edge_rows, const int nin) {
-    const int4 a = own;
-    const bool any_neg = (a.x | a.y | a.z | a.w | right | dn.x | dn.y | dn.z | dn.w) < 0;
-    const unsigned negm = any_neg ? neg4(a) : 0u;
-    // masks of the lower row / right neighbour against the two cached labels (d* become the next row's m*)
-    unsigned d0 = match4(dn, th.c0.label), d1 = match4(dn, th.c1.label);
-    unsigned r0 = right == th.c0.label ? 0xff000000u : 0u, r1 = right == th.c1.label ? 0xff000000u : 0u;
-    unsigned xtra = 0;                 // own pixels accounted for without the cache (>2 labels in the lane)
-    if (((m0 | m1 | negm) & (d0 | d1 | (any_neg ? 0xffffffffu : 0u))) != 0xffffffffu || (!any_neg && !(r0 | r1))) {
-        // Some label around is not cached: load it.  One code instance serves the lane's own pixels,
-        // the right neighbour and the row below (the region that starts there is then already cached
-        // when the walk reaches it).  Entries (re)loaded in this row are pinned.
-        unsigned pinned = 0;
-#pragma unroll 1
-        for (int it = 0; it < 6; ++it) {
-            const unsigned c_own = m0 | m1 | negm | xtra;
-            int cand, i4 = 0;
-            bool for_own = false;
-            if (c_own != 0xffffffffu) {
-                i4 = (__ffs(~c_own) - 1) >> 3;
-                cand = pick4(a, i4);
-                for_own = true;
-            } else if (any_neg) {
-                break;                                    // nodata around: neighbours go through the slow path
-            } else if (!(r0 | r1)) {
-                cand = right;
-            } else if ((d0 | d1) != 0xffffffffu) {
-                cand = pick4(dn, (__ffs(~(d0 | d1)) - 1) >> 3);
-            } else {
-                break;
-            }
-            int which = -1;
-            if (th.c0.label < 0 && !(pinned & 1u)) which = 0;          // an empty entry first
-            else if (th.c1.label < 0 && !(pinned & 2u)) which = 1;
-            else if (m0 == 0 && !(pinned & 1u)) which = 0;             // else one this row's pixels do not use
-            else if (m1 == 0 && !(pinned & 2u)) which = 1;
-            if (which < 0) {
-                if (!for_own) break;                                   // three labels meet here: slow path below
-                STAT(1);
-                Acc<C> one;
-                one.reset(cand);
-                const unsigned bm = (0xffu << (8 * i4)) & vm;
-                acc_pixels<C>(one, bm, TB);
-                if (SPECIAL && bm)
-                    one.border = (left_edge && i4 == 0 ? 1u : 0u) + (i4 == last_k ? 1u : 0u) + edge_rows;
-                acc_push<C>(T, P, one);
-                xtra |= 0xffu << (8 * i4);
-                continue;
-            }
-            STAT(for_own ? 0 : 2);
-            th.evict(T, P, which, cand);
-            const unsigned mm = match4(a, cand), dd = match4(dn, cand), rr = right == cand ? 0xff000000u : 0u;
-            if (which == 0) { m0 = mm; d0 = dd; r0 = rr; pinned |= 1u; }
-            else            { m1 = mm; d1 = dd; r1 = rr; pinned |= 2u; }
-        }
-    }
-    if (any_neg) {                                     // cache labels are >= 0 or EMPTY(-1): keep nodata out
+__device__ __forceinline__ void process_row(Thread<C>& th, const int4 a, const int4 dn, const int right,
+                                            const unsigned* TB, const Tables<C>& T, const Params& P, const unsigned vm,
+                                            const bool left_edge, const int last_k, const unsigned edge_rows) {
+    // ---- statistics ---------------------------------------------------------------------------------
+    unsigned m0 = match4(a, th.c0.label), m1 = match4(a, th.c1.label);
+    unsigned cov = m0 | m1;
+    if ((a.x | a.y | a.z | a.w) < 0) {                  // nodata among the own pixels (EMPTY is negative too)
+        const unsigned negm = neg4(a);
         m0 &= ~negm;
         m1 &= ~negm;
+        cov = m0 | m1 | negm;
     }
-    // ---- accumulate the 4 pixels ---------------------------------------------------------------------
+    if (cov != 0xffffffffu) {
+#pragma unroll 1
+        do {
+            const int cand = pick4(a, (__ffs(~cov) - 1) >> 3);
+            const unsigned mm = match4(a, cand);
+            cov |= mm;
+            if (m0 == 0) {
+                acc_push<C>(T, P, th.c0);
+                th.c0.label = cand;
+                m0 = mm;
+            } else if (m1 == 0) {
+                acc_push<C>(T, P, th.c1);
+                th.c1.label = cand;
+                m1 = mm;
+            } else {                                    // a third label inside the 4 pixels
+                Acc<C> one;
+                one.reset(cand);
+                const unsigned v = SPECIAL ? (mm & vm) : mm;
+                acc_pixels<C>(one, v, TB);
+                if (SPECIAL) one.border = border_sides(v, left_edge, last_k, edge_rows);
+                acc_push<C>(T, P, one);
+            }
+        } while (cov != 0xffffffffu);
+    }
+    __syncwarp();                                       // reconverge before the common part
     {
         const unsigned v0 = SPECIAL ? (m0 & vm) : m0, v1 = SPECIAL ? (m1 & vm) : m1;
         acc_pixels<C>(th.c0, v0, TB);
         acc_pixels<C>(th.c1, v1, TB);
         if (SPECIAL) {
-            if (left_edge) {
-                th.c0.border += v0 & 1u;
-                th.c1.border += v1 & 1u;
-            }
-            if ((unsigned)last_k < 4u) {
-                th.c0.border += (v0 >> (8 * last_k)) & 1u;
-                th.c1.border += (v1 >> (8 * last_k)) & 1u;
-            }
-            if (edge_rows) {                            // warp-uniform: first / last raster row
-                th.c0.border += edge_rows * (__popc(v0) >> 3);
-                th.c1.border += edge_rows * (__popc(v1) >> 3);
-            }
+            th.c0.border += border_sides(v0, left_edge, last_k, edge_rows);
+            th.c1.border += border_sides(v1, left_edge, last_k, edge_rows);
         }
     }
-    // ---- neighbour pairs -----------------------------------------------------------------------------
-    use0 |= m0 | d0 | r0;
-    use1 |= m1 | d1 | r1;
-    if (!any_neg && ((m0 | m1) & (d0 | d1)) == 0xffffffffu && (r0 | r1)) {
-        // every label around is one of the two cached ones: pairs that straddle them are counted
-        // with byte-mask logic, no per-pair work and no divergence
-        const unsigned n0 = (m0 >> 8) | r0, n1 = (m1 >> 8) | r1;
-        const unsigned cross_h = (m0 & n1) | (m1 & n0);
-        unsigned cross_v = (m0 & d1) | (m1 & d0);
-        if (SPECIAL) cross_v &= vm;                     // padded copies right of the image do not pair
-        th.e01 += (__popc(cross_h) + __popc(cross_v)) >> 3;
-        STAT(3);
-    } else {
-        // a third label or nodata nearby: the 8 pairs one by one (bits 0-3 = (x,x+1), 4-7 = (y,y+1))
-        unsigned pm = (a.x != a.y ? 1u : 0u) | (a.y != a.z ? 2u : 0u) | (a.z != a.w ? 4u : 0u) |
-                      (a.w != right ? 8u : 0u) | (a.x != dn.x ? 16u : 0u) | (a.y != dn.y ? 32u : 0u) |
-                      (a.z != dn.z ? 64u : 0u) | (a.w != dn.w ? 128u : 0u);
-        if (SPECIAL) pm &= 0x0fu | (((1u << nin) - 1u) << 4);         // no vertical pairs right of the image
-        STAT(4);
-        while (pm) {
-            const int b = __ffs(pm) - 1;
-            pm &= pm - 1;
-            const int k = b & 3;
+    // ---- neighbour pairs ---------------------------------------------------------------------------------
+    // vertical (y,y+1): the differing pairs of a lane-row nearly always share one (upper, lower) label
+    // pair, so they are counted together with byte masks: one pass per distinct pair
+    unsigned pv = (a.x != dn.x ? 0x000000ffu : 0u) | (a.y != dn.y ? 0x0000ff00u : 0u) | (a.z != dn.z ? 0x00ff0000u : 0u) |
+                  (a.w != dn.w ? 0xff000000u : 0u);
+    if (SPECIAL) pv &= vm;                               // no vertical pairs right of the image
+    if (pv) {
+#pragma unroll 1
+        do {
+            const int k = (__ffs(pv) - 1) >> 3;
+            const int pa = pick4(a, k), pb = pick4(dn, k);
+            const unsigned same = match4(a, pa) & match4(dn, pb) & pv;
+            pv &= ~same;
+            th.pair(T, P, pa, pb, __popc(same) >> 3);
+        } while (pv);
+    }
+    __syncwarp();
+    // horizontal (x,x+1): bits 0-3
+    unsigned ph = (a.x != a.y ? 1u : 0u) | (a.y != a.z ? 2u : 0u) | (a.z != a.w ? 4u : 0u) | (a.w != right ? 8u : 0u);
+    if (ph) {
+#pragma unroll 1
+        do {
+            const int k = __ffs(ph) - 1;
+            ph &= ph - 1;
             const int pa = pick4(a, k);
-            const int pb = b < 4 ? (k == 0 ? a.y : k == 1 ? a.z : k == 2 ? a.w : right) : pick4(dn, k);
+            const int pb = selp(selp(a.y, a.z, k == 0), selp(a.w, right, k == 2), k < 2);
             th.pair(T, P, pa, pb, 1);
-        }
+        } while (ph);
     }
-    own = dn;
-    m0 = d0;
-    m1 = d1;
-    if (any_neg) {                                     // EMPTY(-1) may have matched nodata pixels of the lower row
-        const unsigned nd = ~neg4(dn);
-        m0 &= nd;
-        m1 &= nd;
-    }
+    __syncwarp();
 }
 
 // Drain the warp's tables to global memory (whole warp, convergent).
@@ -668,7 +614,8 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     constexpr int C = CF::C;
     constexpr int TH = CF::TH, NS = CF::NS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    // align by OFFSET (no integer round trip) so that every derived pointer keeps the shared address space
+    unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem + (size_t)warp * CF::WARP_BYTES;       // this warp's private arena
     unsigned* tab = (unsigned*)(wbase + NS * CF::STAGE_BYTES);
@@ -719,19 +666,11 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
         for (int k = 0; k < NS && k < my_units; ++k) issue(k);
     }
 
-#ifdef DM_RAG_STATS
-    unsigned long long t_start;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-#endif
     Thread<C> th;
     th.init();
-    int units_since_drain = 0;
-    int4 own = make_int4(0, 0, 0, 0);
-    unsigned m0 = 0, m1 = 0;            // byte masks of `own` against the two cached labels
-    unsigned use0 = 0, use1 = 0;        // cache entry touched during the current unit (see the GC below)
+    int units_since_flush = 0;
     // (strip, row block) of the current unit, advanced incrementally (column-major order)
     int sx = (int)(u_begin / P.tiles_y), j = (int)(u_begin - (long long)sx * P.tiles_y);
-    bool contiguous = false;
 
     for (int i = 0; i < my_units; ++i) {
         const int st = USE_TMA ? i % NS : 0;
@@ -765,12 +704,8 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
         const int x0 = strip_x0 + 4 * lane;                 // first of this lane's 4 pixels
         // a unit is "special" when it touches an image border: only those pay for border logic
         const bool special = (sx == 0) || (sx == P.tiles_x - 1) || (unit_y0 == 0) || (unit_y0 + TH >= P.rows_own);
+        int4 own = *(const int4*)(L + 4 * lane);
         if (!special) {
-            if (!contiguous) {
-                own = *(const int4*)(L + 4 * lane);
-                m0 = match4(own, th.c0.label);
-                m1 = match4(own, th.c1.label);
-            }
 #pragma unroll 1
             for (int r = 0; r < TH; ++r) {
                 const int4 dn = *(const int4*)(L + (r + 1) * LAB_PITCH + 4 * lane);
@@ -787,7 +722,8 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
                     }
                     band_transpose<C>(W, TB);
                 }
-                process_row<C, false>(th, own, m0, m1, use0, use1, dn, right, TB, T, P, 0xffffffffu, false, -1, 0u, 4);
+                process_row<C, false>(th, own, dn, right, TB, T, P, 0xffffffffu, false, -1, 0u);
+                own = dn;
             }
         } else {
             // Image borders without a separate per-pixel path: pixels right of the image are replaced
@@ -798,20 +734,12 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
             const bool left_edge = (x0 == 0);
             const int last_k = P.W - 1 - x0;                // in [0,3] for the lane holding the last column
             const int last_col = min(P.W - 1 - strip_x0, STRIP_W - 1);
-            if (!contiguous) {
-                own = *(const int4*)(L + 4 * lane);
-                if (nin < 4) {
-                    const int e = L[last_col];
-                    if (nin < 1) own.x = e;
-                    if (nin < 2) own.y = e;
-                    if (nin < 3) own.z = e;
-                    own.w = e;
-                }
-                m0 = match4(own, th.c0.label);
-                m1 = match4(own, th.c1.label);
-                const unsigned nd = ~neg4(own);
-                m0 &= nd;
-                m1 &= nd;
+            if (nin < 4) {
+                const int e = L[last_col];
+                if (nin < 1) own.x = e;
+                if (nin < 2) own.y = e;
+                if (nin < 3) own.z = e;
+                own.w = e;
             }
 #pragma unroll 1
             for (int r = 0; r < TH; ++r) {
@@ -843,28 +771,13 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
                 }
                 const unsigned edge_rows = ((y == 0 && P.top_border) ? 1u : 0u) +
                                            ((!has_dn && y == P.rows_own - 1 && P.bottom_border) ? 1u : 0u);
-                process_row<C, true>(th, own, m0, m1, use0, use1, dn, right, TB, T, P, vm, left_edge, last_k, edge_rows, nin);
+                process_row<C, true>(th, own, dn, right, TB, T, P, vm, left_edge, last_k, edge_rows);
+                own = dn;
             }
         }
 
-        // ---- convergent garbage collection of the label cache --------------------------------------
-        // An entry nothing touched during this unit is pushed out now, by all lanes together, so
-        // that the next miss of such a lane finds an empty entry instead of evicting on its own.
-        if ((!use0 && th.c0.label >= 0) || (!use1 && th.c1.label >= 0)) {
-            th.e01_flush(T, P);
-            if (!use0 && th.c0.label >= 0) {
-                acc_push<C>(T, P, th.c0);
-                th.c0.label = EMPTY_LABEL;
-            }
-            if (!use1 && th.c1.label >= 0) {
-                acc_push<C>(T, P, th.c1);
-                th.c1.label = EMPTY_LABEL;
-            }
-        }
-        use0 = use1 = 0;
         // next unit of this warp's run
-        contiguous = (j + 1 < P.tiles_y);
-        if (contiguous) ++j;
+        if (j + 1 < P.tiles_y) ++j;
         else { j = 0; ++sx; }
 
         // ---- recycle the stage: this warp is its only reader, so it refills it itself ----------
@@ -874,27 +787,19 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
             issue(i + NS);
         }
 
-        // ---- queued evictions -> tables (whole warp, every unit); tables -> global when they fill up ----
-        ++units_since_drain;
-        const bool last = (i + 1 == my_units);
-        const bool forced = units_since_drain >= CF::FLUSH_UNITS || last;
-        if (forced) th.flush_all(T, P);
-        drain_queues<C>(T, P, lane);
-        const unsigned ur = T.used[0], ue = T.used[1];
-        if (ur > RS / 2 || ue > ES / 2 || forced) {
-            if (lane == 0) STAT(6);
-            drain_tables<C>(T, P, lane);
-            units_since_drain = 0;
+        // ---- queued evictions -> tables when the queues fill up; tables -> global when they fill up ----
+        ++units_since_flush;
+        const bool forced = units_since_flush >= CF::FLUSH_UNITS || (i + 1 == my_units);
+        if (forced) {
+            th.flush_all(T, P);
+            units_since_flush = 0;
+        }
+        __syncwarp();
+        if (forced || T.qn[0] > RQ / 2 || T.qn[1] > EQ / 2) {
+            drain_queues<C>(T, P, lane);
+            if (forced || T.used[0] > RS / 2 || T.used[1] > ES / 2) drain_tables<C>(T, P, lane);
         }
     }
-#ifdef DM_RAG_STATS
-    if (lane == 0) {       // per-warp wall time (ns): counts[] must hold 32 + 2 * total_warps entries
-        unsigned long long t_end;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-        P.counters[32 + 2 * gw] = t_start;
-        P.counters[32 + 2 * gw + 1] = t_end;
-    }
-#endif
 }
 
 // ------------------------------------------------------------------------------------ //
