@@ -30,10 +30,9 @@ namespace rag {
 
 constexpr int STRIP_W = 128;            // pixels per warp row: 32 lanes x 4
 constexpr int LAB_PITCH = STRIP_W + 4;  // + halo columns (TMA inner box must be a multiple of 16 B)
-constexpr int NWARPS = 16;              // warps per CTA, each an independent pipeline
 constexpr int RS = 32;                  // region table slots per warp (power of two)
 constexpr int ES = 64;                  // edge table slots per warp (power of two)
-constexpr int RQ = 32;                  // region eviction queue entries per warp (one per lane when drained)
+constexpr int RQ = 32;                  // region eviction queue entries per warp
 constexpr int EQ = 64;                  // edge eviction queue entries per warp
 constexpr int FLUSH_ROWS = 256;         // forced drain period: 128 px * 256 rows * 255^2 < 2^32
 constexpr int EMPTY_LABEL = -1;
@@ -42,12 +41,13 @@ constexpr int SLOT_UNKNOWN = -2, SLOT_NONE = -1;
 
 constexpr int align128(int x) { return (x + 127) / 128 * 128; }
 
-template <int C_, int TH_, int NS_>
+template <int C_, int TH_, int NS_, int NW_>
 struct Cfg {
     static constexpr int C = C_, TH = TH_, NS = NS_;
+    static constexpr int NWARPS = NW_;                       // warps per CTA, each an independent pipeline
     static constexpr int CW = C_ > 0 ? C_ : 1;               // words of image bytes per lane-row
     static constexpr int THREADS = NWARPS * 32;
-    static constexpr int LAB_BOX = align128((TH + 1) * LAB_PITCH * 4);
+    static constexpr int LAB_BOX = align128(TH * LAB_PITCH * 4);
     static constexpr int IMG_ROW_WORDS = STRIP_W * C / 4;    // 32*C
     static constexpr int IMG_BOX = align128(TH * IMG_ROW_WORDS * 4);
     static constexpr int STAGE_BYTES = LAB_BOX + IMG_BOX;
@@ -56,7 +56,7 @@ struct Cfg {
     static constexpr int TABLE_BYTES = align128(TABLE_WORDS * 4 + NS * 8);   // + full barriers
     static constexpr int WARP_BYTES = NS * STAGE_BYTES + TABLE_BYTES;
     static constexpr int SMEM_BYTES = 128 + NWARPS * WARP_BYTES;
-    static constexpr int TX_BYTES = (TH + 1) * LAB_PITCH * 4 + (C > 0 ? TH * IMG_ROW_WORDS * 4 : 0);
+    static constexpr int TX_BYTES = TH * LAB_PITCH * 4 + (C > 0 ? TH * IMG_ROW_WORDS * 4 : 0);
     static constexpr int FLUSH_UNITS = FLUSH_ROWS / TH > 0 ? FLUSH_ROWS / TH : 1;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -412,13 +412,23 @@ __device__ __forceinline__ void band_transpose(const unsigned* W, unsigned* T) {
 
 template <int C>
 struct Thread {
-    Acc<C> c0, c1;              // 2-entry label cache with per-label accumulators (own-row pixels only)
-    unsigned long long ekey;    // 1-entry run cache of the pair counter: a boundary that runs down
-    unsigned ecnt;              // through this lane's column produces the same key row after row
+    Acc<C> c0, c1;              // 2-entry label cache with per-label accumulators
+    unsigned e01;               // pixel pairs seen between c0.label and c1.label (convergent fast path)
+    int4 up;                    // the 4 labels of the row above (vertical pairs are (up, own))
+    unsigned u0, u1;            // byte masks of `up` against the two cached labels
+    int rp, rq;                 // run of the pair that crosses to the next lane: (a.w, right) = (rp, rq)
+    unsigned rcnt;
+    unsigned long long ekey;    // 1-entry run cache of the generic pair path
+    unsigned ecnt;
 
     __device__ __forceinline__ void init() {
         c0.reset(EMPTY_LABEL);
         c1.reset(EMPTY_LABEL);
+        e01 = 0;
+        up = make_int4(0, 0, 0, 0);
+        u0 = u1 = 0;
+        rp = rq = EMPTY_LABEL;
+        rcnt = 0;
         ekey = EMPTY_KEY;
         ecnt = 0;
     }
@@ -426,7 +436,28 @@ struct Thread {
         if (ecnt) edge_push<C>(T, P, ekey, ecnt);
         ecnt = 0;
     }
+    __device__ __forceinline__ void e01_flush(const Tables<C>& T, const Params& P) {
+        if (e01) edge_push<C>(T, P, pack_key(c0.label, c1.label), e01);
+        e01 = 0;
+    }
+    __device__ __forceinline__ void r_flush(const Tables<C>& T, const Params& P) {
+        if (rcnt) edge_push<C>(T, P, pack_key(rp, rq), rcnt);
+        rcnt = 0;
+    }
+    // replace cache entry `which` (0/1) by label l
+    __device__ __forceinline__ void evict(const Tables<C>& T, const Params& P, int which, int l) {
+        e01_flush(T, P);
+        if (which == 0) {
+            acc_push<C>(T, P, c0);
+            c0.label = l;
+        } else {
+            acc_push<C>(T, P, c1);
+            c1.label = l;
+        }
+    }
     __device__ __forceinline__ void flush_all(const Tables<C>& T, const Params& P) {
+        e01_flush(T, P);
+        r_flush(T, P);
         acc_push<C>(T, P, c0);
         acc_push<C>(T, P, c1);
         edge_flush(T, P);
@@ -436,7 +467,7 @@ struct Thread {
         else if (v == c1.label) c1.border += n;
         else slow_region_add_acc<C>(T, P, v, 0, n, nullptr, nullptr);
     }
-    // n pixel pairs between labels a and b (a != b)
+    // generic path: n pixel pairs between labels a and b (a != b)
     __device__ __forceinline__ void pair(const Tables<C>& T, const Params& P, int a, int b, unsigned n) {
         if ((a | b) >= 0) {
             const unsigned long long k = pack_key(a, b);
@@ -450,6 +481,13 @@ struct Thread {
             if (v >= 0) border_add(T, P, v, n);
         }
     }
+    // (re)load the row above (first unit of a run / of a strip)
+    __device__ __forceinline__ void set_up(const int4& row) {
+        up = row;
+        const unsigned nd = ~neg4(row);
+        u0 = match4(row, c0.label) & nd;
+        u1 = match4(row, c1.label) & nd;
+    }
 };
 
 // image-border sides of the pixels in byte mask v (border units only)
@@ -460,21 +498,39 @@ __device__ __forceinline__ unsigned border_sides(unsigned v, bool left_edge, int
     return n;
 }
 
-// One lane-row (4 pixels) of the walk.  Two independent parts:
-//   statistics  the 4 own pixels are accumulated into the two cached labels with byte masks
-//               (no divergence while the lane sees at most two labels); a label that is not
-//               cached replaces an entry this row does not use (its accumulators are pushed to
-//               the warp's eviction queue), a third label inside the 4 pixels is pushed directly;
-//   pairs       the 8 neighbour pairs this lane owns ((x,x+1) and (y,y+1) of its 4 pixels) are
-//               compared; differing ones go one by one through the lane's run cache.
-// SPECIAL = the unit touches an image border: pixels (and vertical pairs) are masked with `vm` and
-// border sides are counted.
+__device__ __forceinline__ unsigned ne4(const int4& a, int b0, int b1, int b2, int b3) {
+    unsigned m = (a.x != b0) ? 0x000000ffu : 0u;
+    m |= (a.y != b1) ? 0x0000ff00u : 0u;
+    m |= (a.z != b2) ? 0x00ff0000u : 0u;
+    m |= (a.w != b3) ? 0xff000000u : 0u;
+    return m;
+}
+
+// One lane-row (4 pixels) of the walk: `a` = the lane's 4 labels, th.up = the 4 labels above them,
+// `right` = the label right of a.w.  The lane owns the 4 pixels' statistics, the 4 horizontal pairs
+// (a.x,a.y) (a.y,a.z) (a.z,a.w) (a.w,right) and the 4 vertical pairs (up.k, a.k).
+//   * In the common case the two cached labels cover every label of `a` and `up` (a region interior,
+//     or the boundary between two regions running through the lane).  Then everything is byte-mask
+//     arithmetic without divergence: masked DP4A accumulation of the 4 pixels into the two entries,
+//     and -- no label comparison needed -- two pixels of one entry are no pair, two pixels of
+//     different entries are a pair of the key (c0, c1), counted by popcount into e01.
+//   * A label of `a` that is not cached replaces the entry neither this row nor the row above uses
+//     (its accumulators go to the warp's eviction queue).  A third label inside the 4 pixels is
+//     pushed directly.
+//   * Pairs with a pixel outside the cache (junctions of three regions, nodata) are compared label
+//     by label and go through the generic path.  The pair that crosses to the next lane is a run
+//     of its own (rp, rq, rcnt): a region boundary that falls between two lanes costs one compare
+//     per row.
+// SPECIAL = the unit touches an image border: statistics are masked with `vs`, vertical pairs with
+// `vp`, and border sides are counted; no_h = a halo row below the tile (vertical pairs only).
 template <int C, bool SPECIAL>
-__device__ __forceinline__ void process_row(Thread<C>& th, const int4 a, const int4 dn, const int right,
-                                            const unsigned* TB, const Tables<C>& T, const Params& P, const unsigned vm,
-                                            const bool left_edge, const int last_k, const unsigned edge_rows) {
-    // ---- statistics ---------------------------------------------------------------------------------
+__device__ __forceinline__ void process_row(Thread<C>& th, const int4 a, const int right, const unsigned* TB,
+                                            const Tables<C>& T, const Params& P, const unsigned vs, const unsigned vp,
+                                            const bool left_edge, const int last_k, const unsigned edge_rows,
+                                            const bool no_h) {
+    const int4 up = th.up;
     unsigned m0 = match4(a, th.c0.label), m1 = match4(a, th.c1.label);
+    unsigned u0 = th.u0, u1 = th.u1;
     unsigned cov = m0 | m1;
     if ((a.x | a.y | a.z | a.w) < 0) {                  // nodata among the own pixels (EMPTY is negative too)
         const unsigned negm = neg4(a);
@@ -482,33 +538,34 @@ __device__ __forceinline__ void process_row(Thread<C>& th, const int4 a, const i
         m1 &= ~negm;
         cov = m0 | m1 | negm;
     }
+    // ---- labels that are not cached -----------------------------------------------------------------------
     if (cov != 0xffffffffu) {
 #pragma unroll 1
         do {
             const int cand = pick4(a, (__ffs(~cov) - 1) >> 3);
             const unsigned mm = match4(a, cand);
             cov |= mm;
-            if (m0 == 0) {
-                acc_push<C>(T, P, th.c0);
-                th.c0.label = cand;
-                m0 = mm;
-            } else if (m1 == 0) {
-                acc_push<C>(T, P, th.c1);
-                th.c1.label = cand;
-                m1 = mm;
-            } else {                                    // a third label inside the 4 pixels
+            // victim: an entry neither this row nor the row above uses, else one this row does not use
+            const int which = (m0 | u0) == 0 ? 0 : (m1 | u1) == 0 ? 1 : m0 == 0 ? 0 : m1 == 0 ? 1 : -1;
+            if (which < 0) {                                         // a third label inside the 4 pixels
                 Acc<C> one;
                 one.reset(cand);
-                const unsigned v = SPECIAL ? (mm & vm) : mm;
+                const unsigned v = SPECIAL ? (mm & vs) : mm;
                 acc_pixels<C>(one, v, TB);
                 if (SPECIAL) one.border = border_sides(v, left_edge, last_k, edge_rows);
                 acc_push<C>(T, P, one);
+            } else {
+                th.evict(T, P, which, cand);
+                const unsigned uu = match4(up, cand);
+                if (which == 0) { m0 = mm; u0 = uu; }
+                else            { m1 = mm; u1 = uu; }
             }
         } while (cov != 0xffffffffu);
     }
     __syncwarp();                                       // reconverge before the common part
+    // ---- statistics ---------------------------------------------------------------------------------------
     {
-        const unsigned v0 = SPECIAL ? (m0 & vm) : m0, v1 = SPECIAL ? (m1 & vm) : m1;
+        const unsigned v0 = SPECIAL ? (m0 & vs) : m0, v1 = SPECIAL ? (m1 & vs) : m1;
         acc_pixels<C>(th.c0, v0, TB);
         acc_pixels<C>(th.c1, v1, TB);
         if (SPECIAL) {
@@ -516,36 +573,61 @@ __device__ __forceinline__ void process_row(Thread<C>& th, const int4 a, const i
             th.c1.border += border_sides(v1, left_edge, last_k, edge_rows);
         }
     }
-    // ---- neighbour pairs ---------------------------------------------------------------------------------
-    // vertical (y,y+1): the differing pairs of a lane-row nearly always share one (upper, lower) label
-    // pair, so they are counted together with byte masks: one pass per distinct pair
-    unsigned pv = (a.x != dn.x ? 0x000000ffu : 0u) | (a.y != dn.y ? 0x0000ff00u : 0u) | (a.z != dn.z ? 0x00ff0000u : 0u) |
-                  (a.w != dn.w ? 0xff000000u : 0u);
-    if (SPECIAL) pv &= vm;                               // no vertical pairs right of the image
-    if (pv) {
+    // ---- neighbour pairs ----------------------------------------------------------------------------------
+    const unsigned acov = m0 | m1, ucov = u0 | u1;
+    unsigned cv = (u0 & m1) | (u1 & m0);                             // vertical pairs (up.k, a.k) across the two labels
+    unsigned ch = (m0 & (m1 >> 8)) | (m1 & (m0 >> 8));               // horizontal pairs (k, k+1), k = 0..2
+    unsigned lv = ~(acov & ucov);                                    // pairs with a pixel outside the cache
+    unsigned lh = ~(acov & (acov >> 8)) & 0x00ffffffu;
+    bool rdiff = a.w != right;
+    if (SPECIAL) {
+        cv &= vp;
+        lv &= vp;
+        if (no_h) {
+            ch = lh = 0;
+            rdiff = false;
+        }
+    }
+    th.e01 += (__popc(ch) + __popc(cv)) >> 3;
+    const bool rsame = rdiff && a.w == th.rp && right == th.rq;
+    th.rcnt += rsame ? 1u : 0u;
+    const bool rnew = rdiff && !rsame;
+    if (lv | lh | (rnew ? 1u : 0u)) {
+        if (lv) {
+            lv &= ne4(a, up.x, up.y, up.z, up.w);
 #pragma unroll 1
-        do {
-            const int k = (__ffs(pv) - 1) >> 3;
-            const int pa = pick4(a, k), pb = pick4(dn, k);
-            const unsigned same = match4(a, pa) & match4(dn, pb) & pv;
-            pv &= ~same;
-            th.pair(T, P, pa, pb, __popc(same) >> 3);
-        } while (pv);
+            while (lv) {
+                const int k = (__ffs(lv) - 1) >> 3;
+                const int pa = pick4(up, k), pb = pick4(a, k);
+                const unsigned same = match4(up, pa) & match4(a, pb) & lv;
+                lv &= ~same;
+                th.pair(T, P, pa, pb, __popc(same) >> 3);
+            }
+        }
+        if (lh) {
+            lh &= ne4(a, a.y, a.z, a.w, a.w);
+#pragma unroll 1
+            while (lh) {
+                const int k = (__ffs(lh) - 1) >> 3;
+                lh &= ~(0xffu << (8 * k));
+                th.pair(T, P, pick4(a, k), selp(selp(a.y, a.z, k == 0), a.w, k < 2), 1);
+            }
+        }
+        if (rnew) {
+            th.r_flush(T, P);
+            if ((a.w | right) >= 0) {
+                th.rp = a.w;
+                th.rq = right;
+                th.rcnt = 1;
+            } else {
+                th.pair(T, P, a.w, right, 1);
+            }
+        }
     }
     __syncwarp();
-    // horizontal (x,x+1): bits 0-3
-    unsigned ph = (a.x != a.y ? 1u : 0u) | (a.y != a.z ? 2u : 0u) | (a.z != a.w ? 4u : 0u) | (a.w != right ? 8u : 0u);
-    if (ph) {
-#pragma unroll 1
-        do {
-            const int k = __ffs(ph) - 1;
-            ph &= ph - 1;
-            const int pa = pick4(a, k);
-            const int pb = selp(selp(a.y, a.z, k == 0), selp(a.w, right, k == 2), k < 2);
-            th.pair(T, P, pa, pb, 1);
-        } while (ph);
-    }
-    __syncwarp();
+    th.up = a;
+    th.u0 = m0;
+    th.u1 = m1;
 }
 
 // Drain the warp's tables to global memory (whole warp, convergent).
@@ -624,7 +706,7 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
 
     // ---- this warp's run of units (unit = TH rows of one strip, column-major order) -------
     const long long total_units = (long long)P.tiles_x * P.tiles_y;
-    const long long gw = (long long)blockIdx.x * NWARPS + warp;
+    const long long gw = (long long)blockIdx.x * CF::NWARPS + warp;
     const long long u_begin = min(total_units, gw * (long long)P.tiles_per_cta);
     const long long u_end = min(total_units, u_begin + P.tiles_per_cta);
     const int my_units = (int)(u_end - u_begin);
@@ -653,17 +735,22 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     __syncwarp();
     if (my_units == 0) return;
 
-    auto issue = [&](int k) {     // lane 0: TMA loads of this warp's k-th unit into stage k % NS
-        const long long u = u_begin + k;
-        const int sx = (int)(u / P.tiles_y), j = (int)(u - (long long)sx * P.tiles_y);
-        const int st = k % NS;
-        unsigned char* sb = wbase + (size_t)st * CF::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[st], (unsigned)CF::TX_BYTES);
-        tma_load_2d(sb, &mapL, sx * STRIP_W, j * TH, &full_bar[st]);
-        if (C > 0) tma_load_2d(sb + CF::LAB_BOX, &mapI, sx * STRIP_W * C / 4, j * TH, &full_bar[st]);
+    // (strip, row block) of the next unit to fetch, advanced incrementally (column-major order)
+    int isx = (int)(u_begin / P.tiles_y), ij = (int)(u_begin - (long long)isx * P.tiles_y), issued = 0;
+    auto issue = [&]() {          // TMA loads of this warp's next unit into stage issued % NS (lane 0 issues)
+        if (lane == 0) {
+            const int st = issued % NS;
+            unsigned char* sb = wbase + (size_t)st * CF::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[st], (unsigned)CF::TX_BYTES);
+            tma_load_2d(sb, &mapL, isx * STRIP_W, ij * TH, &full_bar[st]);
+            if (C > 0) tma_load_2d(sb + CF::LAB_BOX, &mapI, isx * STRIP_W * C / 4, ij * TH, &full_bar[st]);
+        }
+        ++issued;
+        if (ij + 1 < P.tiles_y) ++ij;
+        else { ij = 0; ++isx; }
     };
-    if (USE_TMA && lane == 0) {
-        for (int k = 0; k < NS && k < my_units; ++k) issue(k);
+    if (USE_TMA) {
+        for (int k = 0; k < NS && k < my_units; ++k) issue();
     }
 
     Thread<C> th;
@@ -671,6 +758,7 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
     int units_since_flush = 0;
     // (strip, row block) of the current unit, advanced incrementally (column-major order)
     int sx = (int)(u_begin / P.tiles_y), j = (int)(u_begin - (long long)sx * P.tiles_y);
+    bool contiguous = false;            // th.up / u0 / u1 carry over from the previous unit
 
     for (int i = 0; i < my_units; ++i) {
         const int st = USE_TMA ? i % NS : 0;
@@ -682,7 +770,7 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
         } else {
             // fallback staging for rasters whose pitch/base TMA cannot describe
             __syncwarp();
-            for (int k = lane; k < (TH + 1) * LAB_PITCH; k += 32) {
+            for (int k = lane; k < TH * LAB_PITCH; k += 32) {
                 const int r = k / LAB_PITCH, cidx = k - r * LAB_PITCH;
                 const int gy = unit_y0 + r, gx = strip_x0 + cidx;
                 Lw[k] = (gy < P.rows_avail && gx < P.W) ? P.labels[(int64_t)gy * P.ld + gx] : 0;
@@ -702,14 +790,26 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
         const int* L = Lw;
         const unsigned* I = (const unsigned*)(sb + CF::LAB_BOX);
         const int x0 = strip_x0 + 4 * lane;                 // first of this lane's 4 pixels
+        if (!contiguous) {
+            // first unit of the run / of a strip: the row above comes straight from global memory
+            // (pixels right of the image are copies of the row's last pixel, as below)
+            int4 v = make_int4(0, 0, 0, 0);
+            if (unit_y0 > 0) {
+                const int32_t* row = P.labels + (int64_t)(unit_y0 - 1) * P.ld;
+                v.x = row[min(x0, P.W - 1)];
+                v.y = row[min(x0 + 1, P.W - 1)];
+                v.z = row[min(x0 + 2, P.W - 1)];
+                v.w = row[min(x0 + 3, P.W - 1)];
+            }
+            th.set_up(v);
+        }
         // a unit is "special" when it touches an image border: only those pay for border logic
         const bool special = (sx == 0) || (sx == P.tiles_x - 1) || (unit_y0 == 0) || (unit_y0 + TH >= P.rows_own);
-        int4 own = *(const int4*)(L + 4 * lane);
         if (!special) {
 #pragma unroll 1
             for (int r = 0; r < TH; ++r) {
-                const int4 dn = *(const int4*)(L + (r + 1) * LAB_PITCH + 4 * lane);
-                int right = __shfl_down_sync(0xffffffffu, own.x, 1);
+                const int4 a = *(const int4*)(L + r * LAB_PITCH + 4 * lane);
+                int right = __shfl_down_sync(0xffffffffu, a.x, 1);
                 if (lane == 31) right = L[r * LAB_PITCH + STRIP_W];
                 unsigned W[CF::CW], TB[CF::CW];
                 if (C > 0) {
@@ -722,42 +822,34 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
                     }
                     band_transpose<C>(W, TB);
                 }
-                process_row<C, false>(th, own, dn, right, TB, T, P, 0xffffffffu, false, -1, 0u);
-                own = dn;
+                process_row<C, false>(th, a, right, TB, T, P, 0xffffffffu, 0xffffffffu, false, -1, 0u, false);
             }
         } else {
             // Image borders without a separate per-pixel path: pixels right of the image are replaced
             // by copies of the row's last pixel (so they never differ from a neighbour) and masked out
-            // of the accumulation with `vm`; border sides are added arithmetically.
+            // of the accumulation / the vertical pairs with `vm`; border sides are added arithmetically.
+            // A halo row below the owned rows (row-tile sharding) only contributes its vertical pairs.
             const int nin = min(4, max(0, P.W - x0));       // pixels of this lane inside the image
             const unsigned vm = nin >= 4 ? 0xffffffffu : ((1u << (8 * nin)) - 1u);
             const bool left_edge = (x0 == 0);
             const int last_k = P.W - 1 - x0;                // in [0,3] for the lane holding the last column
             const int last_col = min(P.W - 1 - strip_x0, STRIP_W - 1);
-            if (nin < 4) {
-                const int e = L[last_col];
-                if (nin < 1) own.x = e;
-                if (nin < 2) own.y = e;
-                if (nin < 3) own.z = e;
-                own.w = e;
-            }
 #pragma unroll 1
             for (int r = 0; r < TH; ++r) {
                 const int y = unit_y0 + r;
-                if (y >= P.rows_own) break;
-                const bool has_dn = (y + 1 < P.rows_avail);     // warp-uniform
-                int4 dn = *(const int4*)(L + (r + 1) * LAB_PITCH + 4 * lane);
-                int right = __shfl_down_sync(0xffffffffu, own.x, 1);
-                if (lane == 31) right = L[r * LAB_PITCH + STRIP_W];
+                if (y >= P.rows_avail) break;
+                const bool halo = (y >= P.rows_own);            // warp-uniform
+                int4 a = *(const int4*)(L + r * LAB_PITCH + 4 * lane);
                 if (nin < 4) {                                  // only lanes of the last strip
-                    const int e = L[(r + 1) * LAB_PITCH + last_col];
-                    if (nin < 1) dn.x = e;
-                    if (nin < 2) dn.y = e;
-                    if (nin < 3) dn.z = e;
-                    dn.w = e;
+                    const int e = L[r * LAB_PITCH + last_col];
+                    if (nin < 1) a.x = e;
+                    if (nin < 2) a.y = e;
+                    if (nin < 3) a.z = e;
+                    a.w = e;
                 }
-                if (!has_dn) dn = own;                          // last raster row: no vertical pairs
-                if (x0 + 4 >= P.W) right = own.w;               // nothing to the right of the last column
+                int right = __shfl_down_sync(0xffffffffu, a.x, 1);
+                if (lane == 31) right = L[r * LAB_PITCH + STRIP_W];
+                if (x0 + 4 >= P.W) right = a.w;                 // nothing to the right of the last column
                 unsigned W[CF::CW], TB[CF::CW];
                 if (C > 0) {
                     if (C == 4) {
@@ -770,11 +862,12 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
                     band_transpose<C>(W, TB);
                 }
                 const unsigned edge_rows = ((y == 0 && P.top_border) ? 1u : 0u) +
-                                           ((!has_dn && y == P.rows_own - 1 && P.bottom_border) ? 1u : 0u);
-                process_row<C, true>(th, own, dn, right, TB, T, P, vm, left_edge, last_k, edge_rows);
-                own = dn;
+                                           ((y == P.rows_own - 1 && P.rows_avail == P.rows_own && P.bottom_border) ? 1u : 0u);
+                process_row<C, true>(th, a, right, TB, T, P, halo ? 0u : vm, y == 0 ? 0u : vm, left_edge, last_k,
+                                     halo ? 0u : edge_rows, halo);
             }
         }
+        contiguous = (j + 1 < P.tiles_y);
 
         // next unit of this warp's run
         if (j + 1 < P.tiles_y) ++j;
@@ -782,9 +875,9 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
 
         // ---- recycle the stage: this warp is its only reader, so it refills it itself ----------
         __syncwarp();
-        if (USE_TMA && lane == 0 && i + NS < my_units) {
+        if (USE_TMA && i + NS < my_units) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before async writes
-            issue(i + NS);
+            issue();
         }
 
         // ---- queued evictions -> tables when the queues fill up; tables -> global when they fill up ----
@@ -862,15 +955,15 @@ template <typename CF>
 static int launch(const Params& Pin, bool allow_tma, cudaStream_t s) {
     Params P = Pin;
     P.tiles_x = (int)ceil_div(P.W, STRIP_W);            // strips
-    P.tiles_y = (int)ceil_div(P.rows_own, CF::TH);      // row blocks per strip
+    P.tiles_y = (int)ceil_div(P.rows_avail, CF::TH);    // row blocks per strip (a halo row below counts)
     const long long total = (long long)P.tiles_x * P.tiles_y;
     if (total == 0) return DM_OK;
     // one persistent 16-warp CTA per SM; every warp takes one contiguous run of units
-    const long long max_warps = (long long)num_sms() * NWARPS;
+    const long long max_warps = (long long)num_sms() * CF::NWARPS;
     const long long per = ceil_div(total, max_warps);
     if (per > 0x7fffffff) return DM_ERR_BAD_ARG;
     P.tiles_per_cta = (int)per;
-    const int grid = (int)ceil_div(ceil_div(total, per), NWARPS);
+    const int grid = (int)ceil_div(ceil_div(total, per), CF::NWARPS);
 
     CUtensorMap mapL, mapI;
     memset(&mapL, 0, sizeof(mapL));
@@ -880,7 +973,7 @@ static int launch(const Params& Pin, bool allow_tma, cudaStream_t s) {
     if (CF::C > 0)
         tma = tma && ((uintptr_t)P.image % 16 == 0) && (P.image_pitch % 16 == 0) && (((int64_t)P.W * CF::C) % 4 == 0);
     if (tma)
-        tma = make_map_2d(&mapL, P.labels, (uint64_t)P.W, (uint64_t)P.rows_avail, (uint64_t)P.ld * 4, LAB_PITCH, CF::TH + 1);
+        tma = make_map_2d(&mapL, P.labels, (uint64_t)P.W, (uint64_t)P.rows_avail, (uint64_t)P.ld * 4, LAB_PITCH, CF::TH);
     if (tma && CF::C > 0)
         tma = make_map_2d(&mapI, P.image, (uint64_t)P.W * CF::C / 4, (uint64_t)P.rows_own, (uint64_t)P.image_pitch,
                           CF::IMG_ROW_WORDS, CF::TH);
@@ -904,14 +997,25 @@ static bool allow_tma_env() {
     return !(e && e[0] == '1');
 }
 
+// DM_RAG_CFG=n selects an alternative (rows per unit, stages, warps per CTA) shape for C = 4 (tuning knob).
 int run(const Params& P, int C, cudaStream_t s) {
     const bool tma = allow_tma_env();
+    const char* e = getenv("DM_RAG_CFG");
+    const int v = e ? atoi(e) : 0;
     switch (C) {
-        case 0: return launch<Cfg<0, 8, 2>>(P, tma, s);
-        case 1: return launch<Cfg<1, 4, 3>>(P, tma, s);
-        case 2: return launch<Cfg<2, 4, 2>>(P, tma, s);
-        case 3: return launch<Cfg<3, 4, 2>>(P, tma, s);
-        case 4: return launch<Cfg<4, 4, 2>>(P, tma, s);
+        case 0: return launch<Cfg<0, 8, 2, 16>>(P, tma, s);
+        case 1: return launch<Cfg<1, 4, 3, 16>>(P, tma, s);
+        case 2: return launch<Cfg<2, 4, 2, 16>>(P, tma, s);
+        case 3: return launch<Cfg<3, 4, 2, 16>>(P, tma, s);
+        case 4:
+            switch (v) {
+                case 1: return launch<Cfg<4, 2, 2, 20>>(P, tma, s);
+                case 2: return launch<Cfg<4, 4, 1, 20>>(P, tma, s);
+                case 3: return launch<Cfg<4, 8, 1, 16>>(P, tma, s);
+                case 4: return launch<Cfg<4, 4, 2, 17>>(P, tma, s);
+                case 5: return launch<Cfg<4, 2, 3, 16>>(P, tma, s);
+                default: return launch<Cfg<4, 4, 2, 16>>(P, tma, s);
+            }
         default: return DM_ERR_BAD_ARG;
     }
 }
