@@ -88,22 +88,25 @@ int scan_exclusive_u32(const uint32_t* in, uint32_t* out, const int64_t* n_dev, 
 }
 
 // ------------------------------------------------------------------------------------ //
-// LSD radix sort, 8-bit digits, 3 kernels per pass (tile histogram, offsets, scatter)
+// LSD radix sort, 9-bit digits, 3 kernels per pass (tile histogram, offsets, scatter)
 // ------------------------------------------------------------------------------------ //
+constexpr int RADIX_BITS = 9;
+constexpr int RADIX = 1 << RADIX_BITS;
 
 __device__ __forceinline__ unsigned digit_of(uint64_t key, int id_bits, int shift) {
     uint64_t ck = ((key >> 32) << id_bits) | (key & ((1ull << id_bits) - 1));
-    return (unsigned)(ck >> shift) & 0xffu;
+    return (unsigned)(ck >> shift) & (unsigned)(RADIX - 1);
 }
 
+// hist is digit-major: hist[d * tiles_cap + tile], so that the per-digit scan over tiles is coalesced
 __global__ void __launch_bounds__(SORT_THREADS) radix_hist(const uint64_t* __restrict__ keys,
                                                            const int64_t* __restrict__ n_dev, int id_bits, int shift,
-                                                           uint32_t* __restrict__ hist /*[tiles][256]*/) {
+                                                           uint32_t* __restrict__ hist, int tiles_cap) {
     const int64_t n = *n_dev;
     const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
     if (base >= n) return;
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
+    __shared__ uint32_t h[RADIX];
+    for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) h[i] = 0;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
@@ -111,29 +114,30 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_hist(const uint64_t* __res
         if (idx < n) atomicAdd(&h[digit_of(keys[idx], id_bits, shift)], 1u);
     }
     __syncthreads();
-    hist[(size_t)blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
+    for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) hist[(size_t)i * tiles_cap + blockIdx.x] = h[i];
 }
 
-// One warp per digit (8 blocks x 32 warps): turns the per-tile counts of that digit into an
-// exclusive prefix over tiles (in place) and writes the digit's total to totals[d].  The
-// digit bases (exclusive scan of the 256 totals) are computed by every scatter block itself.
+// One warp per digit: turns the per-tile counts of that digit into an exclusive prefix over tiles
+// (in place) and writes the digit's total to totals[d].  The digit bases (exclusive scan of the
+// totals) are computed by every scatter block itself.
 __global__ void __launch_bounds__(1024) radix_offsets(uint32_t* __restrict__ hist, const int64_t* __restrict__ n_dev,
-                                                      uint32_t* __restrict__ totals) {
+                                                      uint32_t* __restrict__ totals, int tiles_cap) {
     const int64_t n = *n_dev;
     const int tiles = (int)((n + SORT_TILE - 1) / SORT_TILE);
     const int lane = threadIdx.x & 31;
     const int d = blockIdx.x * 32 + (threadIdx.x >> 5);
+    uint32_t* row = hist + (size_t)d * tiles_cap;
     uint32_t carry = 0;
     for (int t0 = 0; t0 < tiles; t0 += 32) {
         const int t = t0 + lane;
-        const uint32_t c = t < tiles ? hist[(size_t)t * 256 + d] : 0;
+        const uint32_t c = t < tiles ? row[t] : 0;
         uint32_t inc = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += v;
         }
-        if (t < tiles) hist[(size_t)t * 256 + d] = carry + inc - c;
+        if (t < tiles) row[t] = carry + inc - c;
         carry += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (lane == 0) totals[d] = carry;
@@ -144,19 +148,31 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter(const uint64_t* __
                                                               uint64_t* __restrict__ kout, uint32_t* __restrict__ vout,
                                                               const int64_t* __restrict__ n_dev, int id_bits, int shift,
                                                               const uint32_t* __restrict__ hist,
-                                                              const uint32_t* __restrict__ totals) {
+                                                              const uint32_t* __restrict__ totals, int tiles_cap) {
     const int64_t n = *n_dev;
     const int64_t tile_base = (int64_t)blockIdx.x * SORT_TILE;
     if (tile_base >= n) return;
     constexpr int NW = SORT_THREADS / 32;
-    __shared__ uint32_t wcnt[NW][256];
-    __shared__ uint32_t goff[256];
+    constexpr int PER = RADIX / SORT_THREADS;             // digits per thread in the block-wide steps
+    __shared__ uint32_t wcnt[NW][RADIX];
+    __shared__ uint32_t goff[RADIX];
     __shared__ uint32_t sm_scan[SORT_THREADS / 32 + 1];
-    for (int i = threadIdx.x; i < NW * 256; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
-    {
+    for (int i = threadIdx.x; i < NW * RADIX; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
+    {   // digit base = exclusive scan of the digit totals (thread t owns digits [t*PER, (t+1)*PER))
+        uint32_t t[PER], sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            t[k] = totals[threadIdx.x * PER + k];
+            sum += t[k];
+        }
         uint32_t tot;
-        const uint32_t base = block_excl_scan<SORT_THREADS>(totals[threadIdx.x], sm_scan, tot);   // digit base
-        goff[threadIdx.x] = base + hist[(size_t)blockIdx.x * 256 + threadIdx.x];
+        uint32_t base = block_excl_scan<SORT_THREADS>(sum, sm_scan, tot);
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int d = threadIdx.x * PER + k;
+            goff[d] = base + hist[(size_t)d * tiles_cap + blockIdx.x];
+            base += t[k];
+        }
     }
     __syncthreads();
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -167,13 +183,16 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter(const uint64_t* __
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const int64_t idx = wbase + i * 32 + lane;
+        key[i] = idx < n ? kin[idx] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int64_t idx = wbase + i * 32 + lane;
         const bool valid = idx < n;
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        key[i] = 0;
         dig[i] = 0;
         rank[i] = 0;
         if (valid) {
-            key[i] = kin[idx];
             dig[i] = digit_of(key[i], id_bits, shift);
             const unsigned peers = __match_any_sync(vmask, dig[i]);
             const int leader = __ffs(peers) - 1;
@@ -188,8 +207,7 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter(const uint64_t* __
         __syncwarp();
     }
     __syncthreads();
-    {   // exclusive prefix over warps, per digit
-        const int d = threadIdx.x;
+    for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) {   // exclusive prefix over warps, per digit
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
@@ -224,8 +242,8 @@ size_t sort_ws_bytes(int64_t cap) {
     size_t b = 0;
     b += align_up((size_t)cap * sizeof(uint64_t), 256);
     b += align_up((size_t)cap * sizeof(uint32_t), 256);
-    b += align_up((size_t)ceil_div(cap, SORT_TILE) * 256 * sizeof(uint32_t), 256);
-    b += align_up(256 * sizeof(uint32_t), 256);
+    b += align_up((size_t)ceil_div(cap, SORT_TILE) * RADIX * sizeof(uint32_t), 256);
+    b += align_up(RADIX * sizeof(uint32_t), 256);
     return b;
 }
 
@@ -236,16 +254,17 @@ int sort_pairs(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t cap
     Carver c(ws);
     uint64_t* k2 = c.take<uint64_t>(cap);
     uint32_t* v2 = c.take<uint32_t>(cap);
-    uint32_t* hist = c.take<uint32_t>((size_t)ceil_div(cap, SORT_TILE) * 256);
-    uint32_t* totals = c.take<uint32_t>(256);
     const unsigned tiles = (unsigned)ceil_div(cap, SORT_TILE);
-    const int passes = (key_bits + 7) / 8;
+    uint32_t* hist = c.take<uint32_t>((size_t)tiles * RADIX);
+    uint32_t* totals = c.take<uint32_t>(RADIX);
+    const int passes = (key_bits + RADIX_BITS - 1) / RADIX_BITS;
     uint64_t *ka = keys, *kb = k2;
     uint32_t *va = vals, *vb = vals ? v2 : nullptr;
     for (int p = 0; p < passes; ++p) {
-        DM_COUNT_LAUNCH(); radix_hist<<<tiles, SORT_THREADS, 0, s>>>(ka, n_dev, id_bits, 8 * p, hist);
-        DM_COUNT_LAUNCH(); radix_offsets<<<8, 1024, 0, s>>>(hist, n_dev, totals);
-        DM_COUNT_LAUNCH(); radix_scatter<<<tiles, SORT_THREADS, 0, s>>>(ka, va, kb, vb, n_dev, id_bits, 8 * p, hist, totals);
+        DM_COUNT_LAUNCH(); radix_hist<<<tiles, SORT_THREADS, 0, s>>>(ka, n_dev, id_bits, RADIX_BITS * p, hist, (int)tiles);
+        DM_COUNT_LAUNCH(); radix_offsets<<<RADIX / 32, 1024, 0, s>>>(hist, n_dev, totals, (int)tiles);
+        DM_COUNT_LAUNCH(); radix_scatter<<<tiles, SORT_THREADS, 0, s>>>(ka, va, kb, vb, n_dev, id_bits, RADIX_BITS * p, hist, totals,
+                                                    (int)tiles);
         uint64_t* tk = ka; ka = kb; kb = tk;
         uint32_t* tv = va; va = vb; vb = tv;
     }
