@@ -246,6 +246,68 @@ def score_l2(mean, edge_keys, norm2=None):
     return scores
 
 
+class PackedMLP:
+    """bf16 weights of a Nets.MLP-structured network (Nets.py:11-35) in the padded tensor-core
+    layout dm_score_mlp_bf16 / dm_mlp_forward_bf16 read (dm_mlp_pack).  hidden <= 256, n_out <= 16."""
+
+    def __init__(self, W1, b1, W2, b2, W3, b3):
+        L = lib()
+        ws = [W1, b1, W2, b2, W3, b3]
+        _need_cuda(*ws)
+        ws = [w.detach().contiguous().float() for w in ws]
+        self.hidden, self.in_features = ws[0].shape
+        self.n_out = ws[4].shape[0]
+        if ws[2].shape != (self.hidden, self.hidden) or ws[4].shape[1] != self.hidden or ws[1].shape != (self.hidden,) \
+                or ws[3].shape != (self.hidden,) or ws[5].shape != (self.n_out,):
+            raise ValueError("weights do not have the Linear(in,h) / Linear(h,h) / Linear(h,out) shapes of Nets.MLP")
+        nbytes = L.dm_mlp_packed_bytes(self.in_features, self.hidden, self.n_out)
+        if nbytes == 0:
+            raise ValueError("unsupported MLP dimensions (hidden <= 256, n_out <= 16)")
+        dev = ws[0].device
+        self.blob = torch.empty(nbytes, dtype=_U8, device=dev)
+        with torch.cuda.device(dev):
+            L.check(L.dm_mlp_pack(*[_p(w) for w in ws], self.in_features, self.hidden, self.n_out, _p(self.blob),
+                                  _stream()), "dm_mlp_pack")
+
+
+def score_mlp(mean, edge_keys, mlp: PackedMLP, want_h2=False, n_edges_dev=None, out=None):
+    """Pair-MLP scores of every edge: x_e = concat(mean[lo], mean[hi]) through the three
+    Linear + leaky_relu layers of Nets.MLP.forward (Nets.py:28-35), bf16 operands / fp32
+    accumulation on tcgen05 -> (o fp32 [E, n_out], h2 fp32 [E, hidden] or None)."""
+    L = lib()
+    _need_cuda(mean, edge_keys)
+    if mean.dtype != _F32 or not mean.is_contiguous():
+        raise ValueError("mean must be a contiguous float32 [R, D] tensor")
+    R, D = mean.shape
+    if mlp.in_features != 2 * D:
+        raise ValueError("the pair-MLP takes concat(mean[lo], mean[hi]): in_features must be 2 D")
+    dev = mean.device
+    E = edge_keys.shape[0]
+    o = out if out is not None else torch.empty((E, mlp.n_out), dtype=_F32, device=dev)
+    h2 = torch.empty((E, mlp.hidden), dtype=_F32, device=dev) if want_h2 else None
+    with torch.cuda.device(dev):
+        n = n_edges_dev if n_edges_dev is not None else torch.tensor([E], dtype=_I64, device=dev)
+        L.check(L.dm_score_mlp_bf16(_p(mean), D, _p(edge_keys.contiguous()), _p(n), E, _p(mlp.blob), mlp.in_features,
+                                    mlp.hidden, mlp.n_out, _p(o), _p(h2), _stream()), "dm_score_mlp_bf16")
+    return o, h2
+
+
+def mlp_forward(x, mlp: PackedMLP, want_h2=True):
+    """Nets.MLP()(x): x fp32 [B, in_features] -> (fc3 [B, n_out], fc2 [B, hidden])."""
+    L = lib()
+    _need_cuda(x)
+    x = x.contiguous().float()
+    B, K = x.shape
+    if K != mlp.in_features:
+        raise ValueError("x has %d features, the network takes %d" % (K, mlp.in_features))
+    o = torch.empty((B, mlp.n_out), dtype=_F32, device=x.device)
+    h2 = torch.empty((B, mlp.hidden), dtype=_F32, device=x.device) if want_h2 else None
+    with torch.cuda.device(x.device):
+        L.check(L.dm_mlp_forward_bf16(_p(x), B, _p(mlp.blob), K, mlp.hidden, mlp.n_out, _p(o), _p(h2), _stream()),
+                "dm_mlp_forward_bf16")
+    return o, h2
+
+
 def relabel(labels, root):
     """labels'[p] = root[labels[p]] (nodata kept)."""
     L = lib()
@@ -379,15 +441,15 @@ class MergeEngine:
         self.counts.zero_()
         self.counts[0] = E
 
-    def merge_loaded_graph(self, tau, max_rounds=64):
+    def merge_loaded_graph(self, tau, max_rounds=64, mlp=None):
         with torch.cuda.device(self.dev):
-            rounds, merges = self._merge_loop(tau, max_rounds)
+            rounds, merges = self._merge_loop(tau, max_rounds, mlp)
             E = int(self.host_counts[0])
         return MergeResult(None, self.parent, rounds, merges, self.keys[:E], self.blen[:E], self.scores[:E], self.area,
                            self.perim, self.sum, self.cnt)
 
     def run(self, labels, feats, tau, *, image=None, xs=None, ys=None, region_of_point=None, max_rounds=64,
-            rows_own=None, top_border=True, bottom_border=True, relabel=True):
+            rows_own=None, top_border=True, bottom_border=True, relabel=True, mlp=None):
         labels = _labels_2d(labels)
         _need_cuda(labels, feats, image, xs, ys, region_of_point)
         if feats.dtype != _F32 or feats.dim() != 2 or feats.shape[1] != self.D or feats.stride(1) != 1:
@@ -399,7 +461,7 @@ class MergeEngine:
                 self._rag(labels, image, rows_own, top_border, bottom_border)
                 self._pool(labels, xs, ys, region_of_point, feats)
                 try:
-                    rounds, merges = self._merge_loop(tau, max_rounds)
+                    rounds, merges = self._merge_loop(tau, max_rounds, mlp)
                     break
                 except OverflowError as ov:            # raw edge list outgrew the capacity: resize, rerun
                     self.cap = int(ov.args[0]) + 1024
@@ -413,19 +475,38 @@ class MergeEngine:
                            self.parent, rounds, merges, self.keys[:E], self.blen[:E], self.scores[:E], self.area,
                            self.perim, self.sum, self.cnt)
 
-    def _merge_loop(self, tau, max_rounds):
+    def _score(self, mlp, only):
+        """scores of the live edges: L2 distance (R6), or the pair-MLP logits (R8) when mlp is given.
+        The MLP re-scores every live edge each round (one tensor-core pass; `only` is ignored)."""
+        L, s, D, cap = self.L, _stream(), self.D, self.cap
+        n_edges = self.counts[0:1]
+        if mlp is None:
+            L.check(L.dm_score_l2(_p(self.mean), _p(self.norm2), D, _p(self.keys), _p(n_edges), cap, _p(only),
+                                  _p(self.scores), s), "dm_score_l2")
+        else:
+            if getattr(self, "logits", None) is None or self.logits.shape != (cap, mlp.n_out):
+                self.logits = torch.empty((cap, mlp.n_out), dtype=_F32, device=self.dev)
+            L.check(L.dm_score_mlp_bf16(_p(self.mean), D, _p(self.keys), _p(n_edges), cap, _p(mlp.blob), mlp.in_features,
+                                        mlp.hidden, mlp.n_out, _p(self.logits), None, s), "dm_score_mlp_bf16")
+
+    def _merge_loop(self, tau, max_rounds, mlp=None):
         L, s, R, D, cap = self.L, _stream(), self.R, self.D, self.cap
         n_edges = self.counts[0:1]
+        if mlp is not None and mlp.in_features != 2 * D:
+            raise ValueError("the pair-MLP takes concat(mean[lo], mean[hi]): in_features must be 2 D")
         self.parent.copy_(self.iota)
         self.alive.fill_(1)
         self.counts[5:8].zero_()
         L.check(L.dm_region_mean(_p(self.sum), _p(self.cnt), R, D, _p(self.mean), _p(self.norm2), None, s), "dm_region_mean")
-        L.check(L.dm_score_l2(_p(self.mean), _p(self.norm2), D, _p(self.keys), _p(n_edges), cap, None, _p(self.scores), s),
-                "dm_score_l2")
+        self._score(mlp, None)
         rounds = merges = 0
         while True:
-            L.check(L.dm_merge_select_l2(_p(self.scores), float(tau), _p(n_edges), cap, _p(self.selected),
-                                         self.counts[4:5].data_ptr(), s), "dm_merge_select_l2")
+            if mlp is None:
+                L.check(L.dm_merge_select_l2(_p(self.scores), float(tau), _p(n_edges), cap, _p(self.selected),
+                                             self.counts[4:5].data_ptr(), s), "dm_merge_select_l2")
+            else:
+                L.check(L.dm_merge_select_mlp(_p(self.logits), mlp.n_out, _p(n_edges), cap, _p(self.selected),
+                                              self.counts[4:5].data_ptr(), s), "dm_merge_select_mlp")
             c = self._read_counts()
             if rounds == 0:
                 if c[3] == 1:
@@ -447,23 +528,23 @@ class MergeEngine:
                                      _p(self.perim), _p(self.ws), self.ws_bytes, s), "dm_edges_rekey")
             L.check(L.dm_region_mean(_p(self.sum), _p(self.cnt), R, D, _p(self.mean), _p(self.norm2), _p(self.changed), s),
                     "dm_region_mean")
-            L.check(L.dm_score_l2(_p(self.mean), _p(self.norm2), D, _p(self.keys), _p(n_edges), cap, _p(self.changed),
-                                  _p(self.scores), s), "dm_score_l2")
+            self._score(mlp, self.changed)
         return rounds, merges
 
 
-def merge_graph(sum_, cnt, area, perimeter, edge_keys, boundary_len, tau, max_rounds=64):
-    """Merge loop on an explicit region graph (spec SURVEY.md section 8(a) R9)."""
+def merge_graph(sum_, cnt, area, perimeter, edge_keys, boundary_len, tau, max_rounds=64, mlp=None):
+    """Merge loop on an explicit region graph (spec SURVEY.md section 8(a) R9): edges with L2 score < tau
+    are contracted, or -- when a PackedMLP is given -- edges whose pair-MLP logit 1 exceeds logit 0."""
     _need_cuda(sum_, cnt, area, perimeter, edge_keys, boundary_len)
     R, D = sum_.shape
     eng = MergeEngine(1, 1, R, D, C=0, n_points=0, edge_capacity=max(edge_keys.shape[0], 1), device=sum_.device)
     with torch.cuda.device(sum_.device):
         eng.load_graph(sum_, cnt, area, perimeter, edge_keys, boundary_len)
-    return eng.merge_loaded_graph(tau, max_rounds)
+    return eng.merge_loaded_graph(tau, max_rounds, mlp)
 
 
 def merge_scene(labels, feats, tau, *, n_regions, image=None, xs=None, ys=None, region_of_point=None, max_rounds=64,
-                engine: Optional[MergeEngine] = None) -> MergeResult:
+                engine: Optional[MergeEngine] = None, mlp=None) -> MergeResult:
     """End to end on one GPU: label raster (+ optional image bands) and sample-point
     embeddings -> merged label map.  Host (CPU / numpy) inputs are staged through pinned
     memory and the label map comes back on the host, so the call is a drop-in for a CPU
@@ -489,7 +570,8 @@ def merge_scene(labels, feats, tau, *, n_regions, image=None, xs=None, ys=None, 
     if engine is None:
         engine = MergeEngine(H, W, n_regions, feats_d.shape[1], C=0 if image_d is None else image_d.shape[2],
                              n_points=feats_d.shape[0], device=labels_d.device)
-    res = engine.run(labels_d, feats_d, tau, image=image_d, xs=xs_d, ys=ys_d, region_of_point=rop_d, max_rounds=max_rounds)
+    res = engine.run(labels_d, feats_d, tau, image=image_d, xs=xs_d, ys=ys_d, region_of_point=rop_d, max_rounds=max_rounds,
+                     mlp=mlp)
     if host:
         res.labels = res.labels.cpu()
         res.root = res.root.cpu()

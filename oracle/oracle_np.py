@@ -485,7 +485,7 @@ def min_root_propagate(n, u, v):
 
 
 def merge_graph(sum_, cnt, area, perim, keys, blen, tau=None, mlp=None, max_rounds=64,
-                components=min_root_propagate):
+                components=min_root_propagate, mlp_bf16=False):
     """Iterative merge loop, spec SURVEY.md section 8(a) R9.
 
     round: score live edges (L2: ExtractFeatures.py:119-147; MLP: Nets.py:28-35) ->
@@ -505,7 +505,7 @@ def merge_graph(sum_, cnt, area, perim, keys, blen, tau=None, mlp=None, max_roun
     while True:
         mean = region_mean(sum_, cnt)
         if mlp is not None:
-            o, _ = mlp_forward(pair_features(mean, keys), *mlp)
+            o, _ = (mlp_forward_bf16 if mlp_bf16 else mlp_forward)(pair_features(mean, keys), *mlp)
             scores = o
             sel = o[:, 1] > o[:, 0] if len(keys) else np.zeros(0, bool)
         else:
