@@ -39,6 +39,16 @@ def measured_peaks():
         return FALLBACK_HBM_GBS, "fallback"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu capture
+    (profiles/traffic.json, written by tools/profile_summary.py for the same workload); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region with NVML (in-process thread,
     ~2 ms period; nvidia-smi is too slow to start for a region this short)."""
@@ -112,26 +122,73 @@ def run_cpu_port(cfg, steps=1, warmup=0):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return float(np.mean(times)), res, sc
+    return float(np.mean(times)), res["merges"], sc["n_regions"]
+
+
+_BARRIER = None
+
+
+def _cpu_init(barrier):
+    global _BARRIER
+    _BARRIER = barrier
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[k] = "1"
+
+
+def _cpu_worker(args):
+    """One process = one sample scene: generate it, meet the others at the barrier, then run the timed steps."""
+    cfg, steps = args
+    from oracle import oracle_np as o
+    sc = o.synth_scene(cfg["H"], cfg["W"], cfg["R"], C=cfg["C"], P=cfg["P"], D=cfg["D"], seed=cfg["seed"])
+    _BARRIER.wait()
+    t0 = time.time()
+    for _ in range(steps):
+        res = o.merge_scene(sc["labels"], sc["n_regions"], sc["region_of_point"], sc["feats"], tau=cfg["tau"])
+        o.pool_bands(sc["labels"], sc["image"], sc["n_regions"])
+    return t0, time.time(), res["merges"], sc["n_regions"]
+
+
+def run_cpu_port_parallel(cfg, steps=1, procs=None):
+    """The oracle port on ALL host cores: the numpy path is single-threaded, so `procs` processes each
+    run it on their own sample scene (different seeds) side by side; throughput = pixels of all
+    samples / (last finish - first start).  Returns (seconds per step, merges of one sample, segments, procs)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64) if procs is None else procs)
+    if procs == 1:
+        sec, merges, R = run_cpu_port(cfg, steps=steps)
+        return sec, merges, R, 1
+    ctx = mp.get_context("spawn")
+    jobs = [(dict(cfg, seed=cfg["seed"] + i), steps) for i in range(procs)]
+    with ctx.Pool(procs, initializer=_cpu_init, initargs=(ctx.Barrier(procs),)) as pool:
+        out = pool.map(_cpu_worker, jobs, chunksize=1)
+    wall = max(o[1] for o in out) - min(o[0] for o in out)
+    return wall / steps, out[0][2], out[0][3], procs
+
+
+def cpu_baseline_record(cfg, side, steps=1):
+    ccfg = cpu_sample_dims(cfg, side)
+    sec, merges, R, procs = run_cpu_port_parallel(ccfg, steps=steps)
+    mpx = procs * ccfg["H"] * ccfg["W"] / sec / 1e6
+    sample = (f"{procs} x {ccfg['H']}x{ccfg['W']} scenes at the workload's region pitch ({R} segments each), "
+              f"{ccfg['C']} bands; numpy oracle port, one process per scene on {procs} of {os.cpu_count()} host cores")
+    return {"value": mpx, "unit": "Mpx/s", "cores": procs, "kind": "port", "sample": sample}, sec, merges * procs
 
 
 def reference_arm(args):
-    cfg = cpu_sample_dims(CFG, args.cpu_side)
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), min(args.warmup, 1)
-    sec, res, sc = run_cpu_port(cfg, steps=steps, warmup=warmup)
-    mpx = cfg["H"] * cfg["W"] / sec / 1e6
-    sample = f"{cfg['H']}x{cfg['W']} scene at the workload's region pitch ({sc['n_regions']} segments), {cfg['C']} bands"
+    steps, warmup = max(1, min(args.steps, 3)), 0
+    rec, sec, merges = cpu_baseline_record(CFG, args.cpu_side, steps=steps)
     line = {
-        "impl": "reference", "metric": "megapixels/sec end-to-end (RAG+pool+score+merge+relabel)", "value": mpx,
+        "impl": "reference", "metric": "megapixels/sec end-to-end (RAG+pool+score+merge+relabel)", "value": rec["value"],
         "unit": "Mpx/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/u8 index + fp32 scores",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": mpx, "unit": "Mpx/s", "cores": 1, "kind": "port", "sample": sample},
-        "e2e": {"value": mpx, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "merged_edges_per_s": res["merges"] / sec,
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": rec["sample"]},
+        "cpu_baseline": rec,
+        "e2e": {"value": rec["value"], "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "merged_edges_per_s": merges / sec,
     }
     print(json.dumps(line), flush=True)
 
@@ -226,14 +283,44 @@ def b200_arm(args):
         e2e_step()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
 
-    # ---- CPU baseline: the oracle port on a bounded sample, same box -----------------------------------
+    # ---- the pair-MLP scorer (R8) on the scene's edges: tcgen05 kernel timed alone ------------------------------
+    mlp_rec = None
+    try:
+        from deepmerge_b200 import PackedMLP
+        g = torch.Generator(device="cpu").manual_seed(1)
+        hid, n_out = 250, 2
+        mk = lambda *sh: (torch.randn(*sh, generator=g) / (sh[-1] ** 0.5)).to(dev)
+        mlp = PackedMLP(mk(hid, 2 * D), mk(hid), mk(hid, hid), mk(hid), mk(n_out, hid), mk(n_out))
+        keys0 = rag.edge_keys.contiguous()
+        n0 = torch.tensor([E0], dtype=torch.int64, device=dev)
+        o_buf = torch.empty((E0, n_out), dtype=torch.float32, device=dev)
+        m0 = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        m1 = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        for i in range(6):
+            m0[i].record()
+            L.check(L.dm_score_mlp_bf16(_p(eng.mean), D, _p(keys0), _p(n0), E0, _p(mlp.blob), 2 * D, hid, n_out, _p(o_buf),
+                                        None, s), "mlp")
+            m1[i].record()
+        torch.cuda.synchronize()
+        mlp_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(m0[1:], m1[1:])]))
+        useful = 2.0 * E0 * (2 * D * hid + hid * hid + hid * n_out)
+        padded = 2.0 * E0 * (256 * 256 + 256 * 256 + 256 * 16)
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                tpeak = float(json.load(f)["bf16_tflops"])
+        except Exception:
+            tpeak = 1590.0
+        mlp_rec = {"kernel": "pair_mlp_kernel (tcgen05, 200->250->250->2 on every edge)", "ms": mlp_ms, "edges": E0,
+                   "tflops_useful": useful / mlp_ms / 1e9, "tflops_padded": padded / mlp_ms / 1e9, "peak_bf16_tflops": tpeak,
+                   "frac_useful": useful / mlp_ms / 1e9 / tpeak, "frac_padded": padded / mlp_ms / 1e9 / tpeak,
+                   "scored_edges_per_s": E0 / (mlp_ms * 1e-3)}
+    except Exception as ex:                              # never hide it: the record says what failed
+        mlp_rec = {"error": repr(ex)}
+
+    # ---- CPU baseline: the oracle port on a bounded sample, same box, all host cores ---------------------------
     cpu = None
     if not args.no_cpu:
-        ccfg = cpu_sample_dims(cfg, min(args.cpu_side, H))
-        sec, cres, csc = run_cpu_port(ccfg)
-        cpu = {"value": ccfg["H"] * ccfg["W"] / sec / 1e6, "unit": "Mpx/s", "cores": 1, "kind": "port",
-               "sample": f"{ccfg['H']}x{ccfg['W']} scene at the workload's region pitch ({csc['n_regions']} segments), "
-                         f"{ccfg['C']} bands; numpy oracle, single thread"}
+        cpu, _, _ = cpu_baseline_record(cfg, min(args.cpu_side, H))
 
     n_roots = int((res.root == torch.arange(R, device=dev, dtype=torch.int32)).sum())
     line = {
@@ -251,8 +338,8 @@ def b200_arm(args):
         "roofline": {"kernel": "rag_pool_kernel (fused RAG + band pooling raster pass)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                      "frac_of_nominal_8TBs": achieved / 8000.0, "ms": rag_ms, "algorithmic_bytes": alg_bytes,
-                     "traffic": None},
-        "cpu_baseline": cpu, "clocks": clocks.summary(),
+                     "traffic": ncu_traffic("rag_pool_kernel") if not args.side else None},
+        "mlp": mlp_rec, "cpu_baseline": cpu, "clocks": clocks.summary(),
     }
     print(json.dumps(line), flush=True)
 
