@@ -103,7 +103,8 @@ __global__ void collect_members_kernel(const int32_t* __restrict__ parent, uint8
 
 // list sorted by (root, member).  The warp that lands on the head of a root's run adds the
 // members' sums into the root's sum one after another (ascending member id): a fixed fp32
-// summation order, so results do not depend on scheduling.
+// summation order, so results do not depend on scheduling.  Each lane keeps up to 4 feature
+// columns in registers and 4 member rows of loads are in flight; the adds stay in order.
 __global__ void __launch_bounds__(256) merge_sums_kernel(const uint64_t* __restrict__ list,
                                                          const int64_t* __restrict__ n_dev, float* __restrict__ sum,
                                                          int D) {
@@ -114,10 +115,35 @@ __global__ void __launch_bounds__(256) merge_sums_kernel(const uint64_t* __restr
     for (int64_t i = warp0; i < n; i += nwarps) {
         const int root = key_lo(list[i]);
         if (i > 0 && key_lo(list[i - 1]) == root) continue;
-        for (int d = lane; d < D; d += 32) {
-            float acc = sum[(int64_t)root * D + d];
-            for (int64_t j = i; j < n && key_lo(list[j]) == root; ++j) acc += sum[(int64_t)key_hi(list[j]) * D + d];
-            sum[(int64_t)root * D + d] = acc;
+        int64_t end = i + 1;                                   // run of this root: [i, end)
+        while (end < n && key_lo(list[end]) == root) ++end;
+        for (int d0 = 0; d0 < D; d0 += 128) {
+            float acc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] = (d0 + lane + 32 * k < D) ? sum[(int64_t)root * D + d0 + lane + 32 * k] : 0.f;
+            int64_t j = i;
+            for (; j + 4 <= end; j += 4) {
+                float v[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float* row = sum + (int64_t)key_hi(list[j + u]) * D + d0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[u][k] = (d0 + lane + 32 * k < D) ? row[lane + 32 * k] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[k] += v[u][k];
+            }
+            for (; j < end; ++j) {
+                const float* row = sum + (int64_t)key_hi(list[j]) * D + d0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (d0 + lane + 32 * k < D) acc[k] += row[lane + 32 * k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (d0 + lane + 32 * k < D) sum[(int64_t)root * D + d0 + lane + 32 * k] = acc[k];
         }
     }
 }

@@ -10,6 +10,8 @@ side = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 R = int(sys.argv[2]) if len(sys.argv) > 2 else int(100000 * side * side / 1e8)
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 C = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+if os.environ.get('DM_LIB'):
+    _lib._LIB = _lib.Library(os.environ['DM_LIB'])
 L = _lib.lib()
 dev = torch.device("cuda:0")
 sc = synth_scene(side, side, R, C=C, device=dev)
