@@ -153,7 +153,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float lrelu(float x) { return x >= 0.f ? x : x * 0.01f; }   // F.leaky_relu default slope
+__device__ __forceinline__ float lrelu(float x) { return fmaxf(x, x * 0.01f); }        // F.leaky_relu, default slope 0.01
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                                // .x = a (low half)
     return *(const uint32_t*)&h;
@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
                 }
             }
             const int D = P.keys ? P.D : P.in_features, K = P.in_features;
+            const bool vec4 = (D % 4 == 0) && (K % 4 == 0) && (P.ld % 4 == 0) && (((uintptr_t)P.src & 15) == 0);
             for (int kc = 0; kc < nk1; ++kc) {
                 mbar_wait(empty(ring.stage), ring.phase ^ 1u, P.status);
                 unsigned char* a_st = smem + OFF_RING + ring.stage * STAGE_BYTES;
@@ -326,12 +327,23 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     float v[8];
+                    if (vec4) {                       // D, ld multiples of 4 and a 16-byte aligned base: 128-bit gathers
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int k = k0 + j;
-                        float x = 0.f;
-                        if (base_lo[it] && k < K) x = k < D ? __ldg(base_lo[it] + k) : __ldg(base_hi[it] + (k - D));
-                        v[j] = x;
+                        for (int q = 0; q < 2; ++q) {
+                            const int k = k0 + 4 * q;
+                            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (base_lo[it] && k < K)
+                                x = k < D ? __ldg((const float4*)(base_lo[it] + k)) : __ldg((const float4*)(base_hi[it] + (k - D)));
+                            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int k = k0 + j;
+                            float x = 0.f;
+                            if (base_lo[it] && k < K) x = k < D ? __ldg(base_lo[it] + k) : __ldg(base_hi[it] + (k - D));
+                            v[j] = x;
+                        }
                     }
                     const int r = w * 32 + it * 4 + rsub;
                     *(uint4*)(a_st + swz(r, piece)) =
