@@ -1125,6 +1125,56 @@ extern "C" int dm_rag_build(const int32_t* labels, int64_t rows_own, int64_t row
     return dm_rag_finish(edge_keys, boundary_len, capacity, n_regions, counts, ws, ws_bytes, stream);
 }
 
+namespace dm {
+namespace rag {
+__global__ void concat_kernel(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ sl,
+                              const int64_t* __restrict__ counts, int n_lists, int64_t slot_cap,
+                              uint64_t* __restrict__ dk, uint32_t* __restrict__ dl, int64_t dst_cap,
+                              int64_t* __restrict__ n_out) {
+    // every thread recomputes the (few) slot offsets; lists are short compared with the grid-stride work
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n_lists * slot_cap;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i / slot_cap);
+        const int64_t j = i - (int64_t)g * slot_cap;
+        if (j >= counts[g]) continue;
+        int64_t off = 0;
+        for (int h = 0; h < g; ++h) off += imin64(counts[h], slot_cap);
+        if (off + j < dst_cap) {
+            dk[off + j] = sk[i];
+            dl[off + j] = sl[i];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int64_t tot = 0, bad = 0;
+        for (int h = 0; h < n_lists; ++h) {
+            if (counts[h] > slot_cap) bad = 1;
+            tot += imin64(counts[h], slot_cap);
+        }
+        if (tot > dst_cap) { bad = 1; tot = dst_cap; }
+        n_out[0] = tot;
+        n_out[1] = bad;
+    }
+}
+}  // namespace rag
+}  // namespace dm
+
+extern "C" int dm_edges_concat(const uint64_t* src_keys, const uint32_t* src_lens, const int64_t* counts, int64_t n_lists,
+                               int64_t slot_capacity, uint64_t* dst_keys, uint32_t* dst_lens, int64_t dst_capacity,
+                               int64_t* n_out_dev, dm_stream_t stream) {
+    if (n_lists < 0 || n_lists > 4096 || slot_capacity < 0 || dst_capacity < 0 || !n_out_dev) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    if (n_lists == 0 || slot_capacity == 0) {
+        DM_CUDA(cudaMemsetAsync(n_out_dev, 0, 2 * sizeof(int64_t), s));
+        return DM_OK;
+    }
+    if (!src_keys || !src_lens || !counts || !dst_keys || !dst_lens) return DM_ERR_BAD_ARG;
+    const unsigned g = (unsigned)imax64(1, imin64(ceil_div(n_lists * slot_capacity, 256), (int64_t)num_sms() * 8));
+    DM_COUNT_LAUNCH(); rag::concat_kernel<<<g, 256, 0, s>>>(src_keys, src_lens, counts, (int)n_lists, slot_capacity, dst_keys,
+                                                         dst_lens, dst_capacity, n_out_dev);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
 extern "C" size_t dm_edges_unique_workspace_bytes(int64_t capacity) {
     const int64_t cap = capacity < 1 ? 1 : capacity;
     return align_up((size_t)cap * 8, 256) + align_up((size_t)cap * 4, 256) + 256 + prims::sort_ws_bytes(cap) +

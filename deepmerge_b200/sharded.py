@@ -5,8 +5,9 @@ pixel pair (y, y+1) belongs to the tile that owns y, so nothing is counted twice
 are global.  One exchange step per phase, with torch.distributed as plumbing (NCCL on the
 GPUs; the same code runs under gloo on CPU tensors, which is how the host logic is tested):
 
-  1. per-tile unique (key, boundary_len) lists: all_gather (padded to the longest) -> every
-     rank sort+uniques the concatenation into the global edge list (replicated);
+  1. per-tile unique (key, boundary_len) lists: all_gather_into_tensor of fixed-capacity slots plus
+     the device-side counts -> dm_edges_concat + dm_edges_sort_unique merge them into the global
+     edge list on every rank (replicated); no length ever travels to the host;
   2. per-region partial statistics: all_reduce(sum) of [area | border | band sums | band
      sums of squares] (int64) and of the pooled embedding sums / point counts;
   3. graph-level work (scoring, union-find merge loop) is small and runs replicated and
@@ -65,57 +66,81 @@ def points_in_tile(ys: torch.Tensor, y0: int, y1: int):
     return torch.nonzero((ys >= y0) & (ys < y1)).flatten()
 
 
-class ShardedMergeEngine:
-    """One rank's share of a scene sharded by rows.  Wraps a MergeEngine sized for the tile."""
+def all_gather_slots(t: torch.Tensor, dist, group=None):
+    """all_gather of equal-sized slots into one tensor [world * len(t)] (one NCCL call, no host sync)."""
+    world = dist.get_world_size(group)
+    out = torch.empty(world * t.shape[0], dtype=t.dtype, device=t.device)
+    if hasattr(dist, "all_gather_into_tensor"):
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    else:                                             # minimal stand-ins used by tests
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t.contiguous(), group=group)
+        out.copy_(torch.cat(parts))
+    return out
 
-    def __init__(self, H, W, n_regions, D, C, n_points_local, dist, device, group=None):
-        from .raster import MergeEngine
+
+class ShardedMergeEngine:
+    """One rank's share of a scene sharded by rows.  Wraps a MergeEngine sized for the tile.
+
+    A step makes no host round trip before the merge loop's own read-back: the per-tile edge lists
+    travel as fixed-capacity slots together with their device-side counts, and overflow / bad-label
+    flags of the tile pass are checked with that first read-back."""
+
+    def __init__(self, H, W, n_regions, D, C, n_points_local, dist, device, group=None, slot_capacity=None):
+        from .raster import MergeEngine, default_edge_capacity
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.H, self.W = H, W
         self.y0, self.y1 = tile_bounds(H, self.world, self.rank)
         self.rows_own = self.y1 - self.y0
         self.has_halo = self.rank < self.world - 1
-        # capacity: the global edge list must fit too
-        from .raster import default_edge_capacity
+        # capacity: the global edge list (and the raw per-tile entries) must fit
         cap = default_edge_capacity(n_regions, H, W)
+        self.slot_cap = int(slot_capacity) if slot_capacity else cap // self.world + 4 * W + 4096
         self.eng = MergeEngine(self.rows_own, W, n_regions, D, C=C, n_points=n_points_local, edge_capacity=cap,
                                device=device)
+        dev = self.eng.dev
+        self.tile_counts = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.cat_counts = torch.zeros(2, dtype=torch.int64, device=dev)
 
     def run(self, labels_tile, feats_local, tau, *, image_tile=None, xs_local=None, ys_local_rel=None, max_rounds=64):
         """labels_tile: int32 [rows_own (+1 halo), W]; ys_local_rel are rows relative to the tile."""
-        from .raster import MergeResult, _p, _stream, merge_edge_lists
+        from .raster import MergeResult, _p, _stream
         e, L, dist = self.eng, self.eng.L, self.dist
         with torch.cuda.device(e.dev):
+            s = _stream()
             e._rag(labels_tile, image_tile, self.rows_own, self.rank == 0, self.rank == self.world - 1)
-            # (1) edges: gather per-tile lists, merge into the replicated global list
-            c = e.counts.tolist()
-            if c[3] == 1:
-                raise ValueError("labels contain ids >= n_regions")
-            if c[2] != 0 or c[3] != 0:
-                raise RuntimeError("tile edge list overflow / pipeline error (capacity %d, needed %d)" % (e.cap, c[1]))
-            E_local = int(c[0])
-            keys, lens = gather_edge_lists(e.keys[:E_local], e.blen[:E_local], dist, self.group)
-            keys, lens = merge_edge_lists(keys, lens, e.R)
-            E = keys.shape[0]
-            if E > e.cap:
-                raise RuntimeError("global edge list exceeds the engine capacity")
-            e.keys[:E].copy_(keys)
-            e.blen[:E].copy_(lens)
-            e.counts.zero_()
-            e.counts[0] = E
+            self.tile_counts.copy_(e.counts[:4])
+            # (1) edges: gather the per-tile lists (fixed slots + device counts), merge into the replicated global list
+            if self.slot_cap > e.cap:
+                raise ValueError("slot capacity exceeds the engine's edge capacity")
+            gk = all_gather_slots(e.keys[: self.slot_cap], dist, self.group)
+            gl = all_gather_slots(e.blen[: self.slot_cap], dist, self.group)
+            gc = all_gather_slots(e.counts[0:1], dist, self.group)
+            L.check(L.dm_edges_concat(_p(gk), _p(gl), _p(gc), self.world, self.slot_cap, _p(e.keys), _p(e.blen), e.cap,
+                                      _p(self.cat_counts), s), "dm_edges_concat")
+            e.counts[:4].zero_()
+            L.check(L.dm_edges_sort_unique(_p(e.keys), _p(e.blen), _p(self.cat_counts), e.cap, e.R, _p(e.counts), _p(e.ws),
+                                           e.ws_bytes, s), "dm_edges_sort_unique")
+            # tile-pass flags ride along with the merge loop's first read-back (counts[2] overflow, counts[3] bad label)
+            e.counts[2:3].copy_(torch.maximum(self.tile_counts[2:3], self.cat_counts[1:2]))
+            e.counts[3:4].copy_(self.tile_counts[3:4])
+            e.counts[1:2].copy_(self.tile_counts[1:2])
             # (2) region statistics: one all-reduce over the fused int64 buffer, then the perimeter
             allreduce_sum_(e.stats, dist, self.group)
-            L.check(L.dm_perimeter(_p(e.keys), _p(e.blen), _p(e.counts), e.cap, _p(e.border), _p(e.perim), e.R, _stream()),
+            L.check(L.dm_perimeter(_p(e.keys), _p(e.blen), _p(e.counts), e.cap, _p(e.border), _p(e.perim), e.R, s),
                     "dm_perimeter")
             # (3) embeddings of the tile's own points -> partial sums -> all-reduce
             e._pool(labels_tile, xs_local, ys_local_rel, None, feats_local)
             allreduce_sum_(e.sum, dist, self.group)
             allreduce_sum_(e.cnt, dist, self.group)
             # (4) replicated merge loop, (5) tile-local relabel
-            rounds, merges = e._merge_loop(tau, max_rounds)
+            try:
+                rounds, merges = e._merge_loop(tau, max_rounds)
+            except OverflowError as ov:
+                raise RuntimeError("tile edge list overflow (capacity %d / slot %d, needed %s)" % (e.cap, self.slot_cap, ov.args[0]))
             L.check(L.dm_relabel(_p(labels_tile), self.rows_own, self.W, labels_tile.stride(0), _p(e.parent), e.R, _p(e.out),
-                                 self.W, _stream()), "dm_relabel")
+                                 self.W, s), "dm_relabel")
             Ef = int(e.host_counts[0])
         return MergeResult(e.out[: self.rows_own], e.parent, rounds, merges, e.keys[:Ef], e.blen[:Ef], e.scores[:Ef], e.area,
                            e.perim, e.sum, e.cnt)

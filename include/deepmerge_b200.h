@@ -118,6 +118,15 @@ size_t dm_edges_unique_workspace_bytes(int64_t capacity);
 int dm_edges_sort_unique(uint64_t* keys, uint32_t* lens, const int64_t* n_in_dev, int64_t capacity,
                          int64_t n_regions, int64_t* n_out_dev, void* ws, size_t ws_bytes, dm_stream_t stream);
 
+/* Concatenate `n_lists` edge lists that sit in equal-sized slots of one buffer (slot g = entries
+ * [g*slot_capacity, g*slot_capacity + counts[g])), e.g. the all-gathered per-tile lists of a sharded scene,
+ * into dst (valid entries only, slot order kept); n_out_dev[0] = total.  counts: int64 [n_lists] on the
+ * device.  No host round trip: the lengths never leave the GPU.  A slot count above slot_capacity or a
+ * total above dst_capacity sets n_out_dev[1] = 1 (n_out_dev has 2 entries). */
+int dm_edges_concat(const uint64_t* src_keys, const uint32_t* src_lens, const int64_t* counts, int64_t n_lists,
+                    int64_t slot_capacity, uint64_t* dst_keys, uint32_t* dst_lens, int64_t dst_capacity,
+                    int64_t* n_out_dev, dm_stream_t stream);
+
 /* perimeter[r] = border[r] + sum of boundary_len over edges incident to r. */
 int dm_perimeter(const uint64_t* edge_keys, const uint32_t* boundary_len, const int64_t* n_edges_dev,
                  int64_t capacity, const int64_t* border, int64_t* perimeter, int64_t n_regions,
