@@ -2,19 +2,22 @@
 // 5th-generation tensor cores: three Linear + leaky_relu(0.01), bf16 operands, fp32 accumulation
 // in TMEM.
 //
-// One persistent CTA per SM walks over tiles of 128 rows (edges).  Six warps, three roles:
+// One persistent CTA per SM walks over tiles of 128 rows (edges).  Fourteen warps, four roles:
 //   warp 0      weight loader: streams the pre-packed bf16 weight chunks (K = 64 columns of all
 //               256 output features, 32 KB, already in the UMMA SWIZZLE_128B K-major image) from
 //               global memory into a 3-stage shared-memory ring with 1-D TMA bulk copies
 //               (cp.async.bulk + mbarrier complete_tx);
 //   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256 / 16, K=16) on the ring's
 //               A / B chunks, tcgen05.commit releases ring stages and signals the accumulator;
-//               owns the TMEM allocation (512 columns: D1 at 0, D2 at 256, D3 at 0);
-//   warps 2-5   workers: (layer 1) gather the tile's rows -- x_e = concat(mean[lo], mean[hi]) --
-//               convert to bf16 and write them as swizzled A chunks into the ring; (epilogues)
-//               tcgen05.ld the accumulator (each warp its TMEM lane quadrant), add the bias, apply
-//               the leaky ReLU, and either re-pack the activations as the next layer's bf16 A
-//               operand in shared memory or store the fp32 result.
+//               owns the TMEM allocation (512 columns: D1 at 0, D2 and then D3 at 256).  Layer 1 of
+//               the NEXT tile is issued between layers 2 and 3 of this one, so the tensor core works
+//               while the epilogue warps are busy;
+//   warps 2-9   epilogue: tcgen05.ld the accumulator (each warp its TMEM lane quadrant), add the bias,
+//               apply the leaky ReLU, and either re-pack the activations as the next layer's bf16 A
+//               operand in shared memory or store the fp32 result;
+//   warps 10-13 producers (layer 1): gather the tile's rows -- x_e = concat(mean[lo], mean[hi]) --
+//               convert to bf16 and write them as swizzled A chunks into the ring, running ahead of
+//               the tile in flight as far as the ring allows.
 // Layers 2 and 3 never leave the SM: h1 and h2 go TMEM -> registers -> shared memory -> tensor core.
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -40,10 +43,11 @@ constexpr int OFF_A2 = OFF_RING + STAGES * STAGE_BYTES;
 constexpr int OFF_W3 = OFF_A2 + A2_BYTES;
 constexpr int OFF_BIAS = OFF_W3 + W3_BYTES;
 constexpr int OFF_BARS = OFF_BIAS + BIAS_FLOATS * 4;
-constexpr int N_BARS = 3 * STAGES + 2;                       // full_b, full_a, empty per stage; d_full; a_ready
+constexpr int N_BARS = 3 * STAGES + 5;                       // full_b, full_a, empty per stage; d1/d2/d3_full; a1/a2_ready
 constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
 constexpr int SMEM_BYTES = 1024 + OFF_TMEM + 16;
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                 // two per TMEM lane quadrant, each half of the columns
+constexpr int THREADS = (2 + EPI_WARPS + 4) * 32;   // loader, MMA issuer, epilogue warps, 4 producer warps
 constexpr int TMEM_COLS = 512;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_A2 % 1024 == 0 && OFF_W3 % 1024 == 0 && STAGE_BYTES % 1024 == 0 && A_CHUNK_BYTES % 1024 == 0, "swizzle atoms");
@@ -184,7 +188,9 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
     auto full_b = [&](int s) { return bar0 + 8u * s; };
     auto full_a = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
-    const uint32_t d_full = bar0 + 8u * (3 * STAGES), a_ready = bar0 + 8u * (3 * STAGES + 1);
+    // accumulator / activation hand-offs, each completing once per tile (parity = tile iteration & 1)
+    const uint32_t d1_full = bar0 + 8u * (3 * STAGES), d2_full = d1_full + 8u, d3_full = d1_full + 16u;
+    const uint32_t a1_ready = d1_full + 24u, a2_ready = d1_full + 32u;
 
     const int64_t n_rows = P.n_dev ? *P.n_dev : P.n_host;
     const int64_t tiles = (n_rows + M_TILE - 1) / M_TILE;
@@ -202,8 +208,11 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
             mbar_init(full_a(s), 4);
             mbar_init(empty(s), 1);
         }
-        mbar_init(d_full, 1);
-        mbar_init(a_ready, 4);
+        mbar_init(d1_full, 1);
+        mbar_init(d2_full, 1);
+        mbar_init(d3_full, 1);
+        mbar_init(a1_ready, EPI_WARPS);
+        mbar_init(a2_ready, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -236,12 +245,12 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
         }
     } else if (warp == 1) {
         // ===== MMA issuer ========================================================================
+        // Issue order: L1(0) | L2(0) L1(1) L3(0) | L2(1) L1(2) L3(1) | ...  Layer 1 of the NEXT tile runs on the
+        // tensor core while the epilogue warps are busy with this tile's h2 (D1 is free once E1 has read it).
         Ring ring;
-        unsigned a_phase = 0;
         unsigned fa_bits = 0;             // full_a[s] completes on layer-1 ring uses only: its own phase per stage
         constexpr uint32_t idesc_hid = umma_idesc(M_TILE, N_HID), idesc_out = umma_idesc(M_TILE, N_OUT);
-        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            // layer 1: D1 = X W1^T, both operands from the ring
+        auto issue_l1 = [&]() {           // D1 = X W1^T, both operands from the ring
             for (int kc = 0; kc < nk1; ++kc) {
                 mbar_wait(full_b(ring.stage), ring.phase, P.status);
                 mbar_wait(full_a(ring.stage), (fa_bits >> ring.stage) & 1u, P.status);
@@ -253,14 +262,17 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
                     for (int k = 0; k < KC / UMMA_K; ++k)
                         tc_mma(tmem, umma_desc(a0 + k * 32), umma_desc(b0 + k * 32), idesc_hid, (kc | k) ? 1u : 0u);
                     tc_commit(empty(ring.stage));
-                    if (kc == nk1 - 1) tc_commit(d_full);
+                    if (kc == nk1 - 1) tc_commit(d1_full);
                 }
                 __syncwarp();
                 ring.advance();
             }
+        };
+        if ((int64_t)blockIdx.x < tiles) issue_l1();
+        unsigned it = 0;
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
             // layer 2: D2 = h1 W2^T, A from the resident activation buffer, B from the ring
-            mbar_wait(a_ready, a_phase, P.status);
-            a_phase ^= 1u;
+            mbar_wait(a1_ready, it & 1u, P.status);
             tc_fence_after();
             for (int kc = 0; kc < nk2; ++kc) {
                 mbar_wait(full_b(ring.stage), ring.phase, P.status);
@@ -272,32 +284,30 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
                     for (int k = 0; k < KC / UMMA_K; ++k)
                         tc_mma(tmem + N_HID, umma_desc(a0 + k * 32), umma_desc(b0 + k * 32), idesc_hid, (kc | k) ? 1u : 0u);
                     tc_commit(empty(ring.stage));
-                    if (kc == nk2 - 1) tc_commit(d_full);
+                    if (kc == nk2 - 1) tc_commit(d2_full);
                 }
                 __syncwarp();
                 ring.advance();
             }
-            // layer 3: D3 = h2 W3^T, both operands resident
-            mbar_wait(a_ready, a_phase, P.status);
-            a_phase ^= 1u;
+            if (tile + gridDim.x < tiles) issue_l1();          // next tile's layer 1 overlaps this tile's epilogue 2
+            // layer 3: D3 = h2 W3^T, both operands resident; D3 takes over D2's columns (E2 has read them)
+            mbar_wait(a2_ready, it & 1u, P.status);
             tc_fence_after();
             if (lane == 0) {
                 for (int kc = 0; kc < nk2; ++kc) {
                     const uint32_t a0 = sbase + OFF_A2 + kc * A_CHUNK_BYTES, b0 = sbase + OFF_W3 + kc * W3_CHUNK_BYTES;
 #pragma unroll
                     for (int k = 0; k < KC / UMMA_K; ++k)
-                        tc_mma(tmem, umma_desc(a0 + k * 32), umma_desc(b0 + k * 32), idesc_out, (kc | k) ? 1u : 0u);
+                        tc_mma(tmem + N_HID, umma_desc(a0 + k * 32), umma_desc(b0 + k * 32), idesc_out, (kc | k) ? 1u : 0u);
                 }
-                tc_commit(d_full);
+                tc_commit(d3_full);
             }
             __syncwarp();
         }
-    } else {
-        // ===== workers: A producer of layer 1, then the three epilogues ===========================
+    } else if (warp >= 2 + EPI_WARPS) {
+        // ===== producers: gather the tile's rows, convert to bf16, write swizzled A chunks (layer 1) ========
         Ring ring;
-        unsigned d_phase = 0;
-        const int w = warp - 2;                       // 0..3
-        const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int w = warp - (2 + EPI_WARPS);         // 0..3
         const int piece = lane & 7, rsub = lane >> 3; // 16-byte piece / row within a 4-row group
         for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int64_t row0 = tile * M_TILE;
@@ -354,20 +364,31 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
                 if (lane == 0) mbar_arrive(full_a(ring.stage));
                 ring.advance();
             }
-            ring.advance(nk2);                        // layer 2's ring uses carry no A chunk
-
+            // layer 2's ring uses carry no A chunk, but the producers still pace themselves on them: running more
+            // than one ring round ahead of the MMA warp would alias the mbarrier phase parity
+            for (int kc = 0; kc < nk2; ++kc) {
+                mbar_wait(empty(ring.stage), ring.phase ^ 1u, P.status);
+                ring.advance();
+            }
+        }
+    } else {
+        // ===== epilogue warps: accumulator -> bias, leaky ReLU -> next layer's A operand / result ============
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;             // which half of the 256 columns this warp handles
+        unsigned it = 0;
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+            const int64_t row0 = tile * M_TILE;
             const int r = quad * 32 + lane;           // accumulator row of this thread
             const int64_t e = row0 + r;
             const uint32_t t_row = tmem + ((uint32_t)(quad * 32) << 16);
             // ---- epilogue 1 / 2: h = lrelu(D + b) -> bf16 A operand (and fp32 h2) ---------------------
 #pragma unroll 1
             for (int layer = 0; layer < 2; ++layer) {
-                mbar_wait(d_full, d_phase, P.status);
-                d_phase ^= 1u;
+                mbar_wait(layer == 0 ? d1_full : d2_full, it & 1u, P.status);
                 tc_fence_after();
                 const float* b = bias + layer * N_HID;
 #pragma unroll 1
-                for (int c0 = 0; c0 < N_HID; c0 += 32) {
+                for (int c0 = half * (N_HID / 2); c0 < (half + 1) * (N_HID / 2); c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(t_row + layer * N_HID + c0, v);
                     tmem_ld_wait();
@@ -390,15 +411,15 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
                 tc_fence_before();
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a_ready);
+                if (lane == 0) mbar_arrive(layer == 0 ? a1_ready : a2_ready);
             }
             // ---- epilogue 3: o = lrelu(D3 + b3) ------------------------------------------------------
-            mbar_wait(d_full, d_phase, P.status);
-            d_phase ^= 1u;
+            // every epilogue warp waits (the next tile's h1 must not overwrite h2 before layer 3 has read it)
+            mbar_wait(d3_full, it & 1u, P.status);
             tc_fence_after();
-            {
+            if (half == 0) {
                 uint32_t v[16];
-                tmem_ld16(t_row, v);
+                tmem_ld16(t_row + N_HID, v);
                 tmem_ld_wait();
                 if (e < n_rows) {
                     const float* b = bias + 2 * N_HID;
