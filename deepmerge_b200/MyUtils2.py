@@ -70,3 +70,64 @@ class PolygonConnectPointDataset:
         """Packed (min << 32) | max keys of the kept rows, in file order (duplicates kept)."""
         lr = np.asarray([[d[2], d[3]] for d in self.data], np.int64).reshape(-1, 2)
         return (np.minimum(lr[:, 0], lr[:, 1]) << 32) | np.maximum(lr[:, 0], lr[:, 1])
+
+
+# --------------------------------------------------------------------------------------------
+# Geometry conventions of ExtractFeatureDataset (MyUtils2.py:213-437) that the raster path must
+# reproduce when it maps sample points to pixels (SURVEY.md section 8(a) R12).  Vectorised over
+# points; integer truncation follows Python's int() (toward zero) like the reference.
+# --------------------------------------------------------------------------------------------
+SCALES = (32, 64, 128, 1)          # config.py:32 `configs.scales`
+
+
+def geo_to_pixel(geo_transform, X, Y):
+    """Sample-point coordinates -> (XPixel, YLine) as the reference computes them, MyUtils2.py:241-242:
+    int(abs((gt[0] - X) / gt[1]) + 1) -- note the +1 -- and the same with gt[3], gt[5] for rows."""
+    gt = geo_transform
+    X, Y = np.asarray(X, np.float64), np.asarray(Y, np.float64)
+    px = np.trunc(np.abs((gt[0] - X) / gt[1]) + 1).astype(np.int64)
+    ln = np.trunc(np.abs((gt[3] - Y) / gt[5]) + 1).astype(np.int64)
+    return px, ln
+
+
+def calculate_left_top_point_and_size(midPointX, midPointY, windowLength):
+    """Window (left, top, w, h) centred on a pixel, MyUtils2.py:379-383: int(mid - w / 2) truncates toward zero."""
+    mx, my, w = (np.asarray(v) for v in (midPointX, midPointY, windowLength))
+    left = np.trunc(mx - w / 2).astype(np.int64)
+    top = np.trunc(my - w / 2).astype(np.int64)
+    w = np.trunc(w).astype(np.int64)
+    if left.ndim == 0:
+        return int(left), int(top), int(w), int(w)
+    return left, top, w, w
+
+
+def get_scales(inner_scale, object_scale, cfg_scales=SCALES):
+    """The four window sizes [inner, object, object + d, object + 2 d], d = int(object - inner), and their
+    factors size / configs.scales[i] (MyUtils2.py:300-327)."""
+    interval = int(object_scale - inner_scale)
+    scales = [inner_scale, object_scale, object_scale + interval, object_scale + 2 * interval]
+    factors = [s * 1.0 / c for s, c in zip(scales, cfg_scales)]
+    return scales, factors
+
+
+def cut_image(image, window):
+    """Zero-padded window of a [C, H, W] uint8 raster, MyUtils2.py:330-360, including the reference's clamp
+    `start + size >= src -> size = src - start` (so a window that ends exactly at the border is cut the same)."""
+    x0, y0, w, h = (int(v) for v in window)
+    C, H, W = image.shape
+    out = np.zeros((C, h, w), np.uint8)
+    ox = oy = 0
+    dw, dh = w, h
+    if x0 < 0:
+        dw += x0
+        ox, x0 = -x0, 0
+    if x0 + dw >= W:
+        dw = W - x0
+    if y0 < 0:
+        dh += y0
+        oy, y0 = -y0, 0
+    if y0 + dh >= H:
+        dh = H - y0
+    if dw > 0 and dh > 0:
+        out[:, oy:oy + dh, ox:ox + dw] = image[:, y0:y0 + dh, x0:x0 + dw]
+    return out

@@ -4,6 +4,7 @@ import os
 import random
 
 import numpy as np
+import pytest
 
 from deepmerge_b200 import MyUtils1, MyUtils2
 from oracle.ref_shim import FakeFeature, FakeLayer, FakeRaster
@@ -44,3 +45,36 @@ def test_pair_sampler_reproduces_reference_under_the_same_seed(golden_dir, tmp_p
     assert np.array_equal(left, g["out_left"]) and np.array_equal(right, g["out_right"]) and np.array_equal(flag, g["out_flag"])
     assert [d[0] for d in data] == g["out_tile"].tolist()
     assert g["counts"].tolist() == [len(g["pos_pairs"]), len(g["pos_pairs"]), len(g["neg_pairs"]), len(g["neg_pairs"])]
+
+
+def test_geometry_helpers_match_reference_golden(golden_dir):
+    """R12: pixel mapping (+1), window placement, scale factors and the zero-padded cutter against values
+    produced by executing MyUtils2.ExtractFeatureDataset (oracle/gen_golden.py:golden_geometry)."""
+    from deepmerge_b200 import MyUtils2 as m
+    g = np.load(os.path.join(golden_dir, "geometry.npz"))
+    px, ln = m.geo_to_pixel(tuple(g["gt"]), g["geo"][:, 0], g["geo"][:, 1])
+    assert np.array_equal(np.stack([px, ln], 1), g["px"])
+    for (x, y, w), want in zip(g["mids"], g["wins"]):
+        assert m.calculate_left_top_point_and_size(int(x), int(y), int(w)) == tuple(int(v) for v in want)
+    left, top, w, h = m.calculate_left_top_point_and_size(g["mids"][:, 0], g["mids"][:, 1], g["mids"][:, 2])
+    assert np.array_equal(np.stack([left, top, w, h], 1), g["wins"])
+    assert tuple(g["cfg_scales"]) == m.SCALES
+    for (a, b), s, f in zip(g["io"], g["scales"], g["factors"]):
+        sc, fa = m.get_scales(int(a), int(b))
+        assert sc == [int(v) for v in s] and np.allclose(fa, f, rtol=0, atol=0)
+    for i, win in enumerate(g["wins"]):
+        assert np.array_equal(m.cut_image(g["arr"], win), g[f"cut{i}"])
+
+
+def test_join_adjacency_form():
+    """R2: `join` lists include the polygon itself (MyUtils.py:110-114); keys come out canonical."""
+    from deepmerge_b200 import MyUtils as m
+    from oracle import oracle_np as o
+    joins = ["0,1,2", "0,1", "2,0,3", "3,2"]
+    assert m.neighbours_from_join(joins[2], 2) == o.neighbours_from_join(joins[2], 2) == [0, 3]
+    keys = m.edge_keys_from_join(joins)
+    assert np.array_equal(keys.view(np.uint64), o.pack_keys(np.array([0, 0, 2]), np.array([1, 2, 3])))
+    with pytest.raises(ValueError):
+        m.neighbours_from_join("1,2", 5)            # self missing: list.remove raises like the reference
+    off, ids = m.membership_from_points(["4,9", "", "7"])
+    assert off.tolist() == [0, 2, 2, 3] and ids.tolist() == [4, 9, 7]
