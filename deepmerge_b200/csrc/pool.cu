@@ -159,6 +159,60 @@ __global__ void __launch_bounds__(256) pool_dense_kernel(const int32_t* __restri
     }
 }
 
+// Per-boundary pooling of a dense embedding grid (north-star "per-boundary feature vectors"; the reference
+// only writes a scalar per boundary, ExtractFeatures.py:217-219).  For every 4-adjacent pixel pair whose two
+// valid labels differ, both pixels' embeddings are added to the edge of that label pair.  A warp takes 32
+// consecutive pixels of a row; lanes flag their (right, down) pairs, then the warp serves the flagged pairs
+// one after another: the edge index comes from a binary search in the sorted unique edge keys (every lane
+// runs the same search: no divergence), and the lanes add the two embedding rows slice by slice.
+template <typename T>
+__global__ void __launch_bounds__(256) pool_boundary_kernel(const int32_t* __restrict__ labels, int64_t H, int64_t W,
+                                                            int64_t ld, int64_t rows_avail, const T* __restrict__ emb,
+                                                            int D, const uint64_t* __restrict__ keys,
+                                                            const int64_t* __restrict__ n_edges_dev,
+                                                            float* __restrict__ bsum, int32_t* __restrict__ bcnt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t E = *n_edges_dev;
+    const int64_t chunks_per_row = (W + 31) / 32;
+    const int64_t total = H * chunks_per_row;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = warp0; w < total; w += nwarps) {
+        const int64_t y = w / chunks_per_row;
+        const int64_t x = (w - y * chunks_per_row) * 32 + lane;
+        int a = -1, r = -1, d = -1;
+        if (x < W) {
+            a = labels[y * ld + x];
+            if (x + 1 < W) r = labels[y * ld + x + 1];
+            if (y + 1 < rows_avail) d = labels[(y + 1) * ld + x];
+        }
+        const bool pr = a >= 0 && r >= 0 && a != r, pd = a >= 0 && d >= 0 && a != d;
+        unsigned mr = __ballot_sync(0xffffffffu, pr), md = __ballot_sync(0xffffffffu, pd);
+        for (int dir = 0; dir < 2; ++dir) {
+            unsigned m = dir == 0 ? mr : md;
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int la = __shfl_sync(0xffffffffu, a, src);
+                const int lb = __shfl_sync(0xffffffffu, dir == 0 ? r : d, src);
+                const uint64_t key = pack_key(la, lb);
+                int64_t lo = 0, hi = E;                       // first index with keys[i] >= key
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (keys[mid] < key) lo = mid + 1;
+                    else hi = mid;
+                }
+                if (lo >= E || keys[lo] != key) continue;     // not an edge of this list (e.g. a foreign tile's)
+                const int64_t xp = (w - y * chunks_per_row) * 32 + src;
+                const T* e0 = emb + (y * W + xp) * (int64_t)D;
+                const T* e1 = dir == 0 ? e0 + D : e0 + W * (int64_t)D;
+                for (int k = lane; k < D; k += 32) atomicAdd(&bsum[lo * D + k], (float)e0[k] + (float)e1[k]);
+                if (lane == 0) atomicAdd(&bcnt[lo], 2);
+            }
+        }
+    }
+}
+
 static unsigned grid_for(int64_t work_items, int threads, int per_sm) {
     int64_t g = ceil_div(work_items, threads);
     int64_t cap = (int64_t)num_sms() * per_sm;
@@ -273,4 +327,25 @@ extern "C" int dm_pool_dense(const int32_t* labels, int64_t H, int64_t W, int64_
     if (!labels || !emb || !sum || !cnt) return DM_ERR_BAD_ARG;
     if (dtype_bf16) return pool_dense_t<__nv_bfloat16>(labels, H, W, ld, (const __nv_bfloat16*)emb, D, R, sum, cnt, S(stream));
     return pool_dense_t<float>(labels, H, W, ld, (const float*)emb, D, R, sum, cnt, S(stream));
+}
+
+extern "C" int dm_pool_boundary(const int32_t* labels, int64_t rows_own, int64_t rows_avail, int64_t W, int64_t ld,
+                                const void* emb, int dtype_bf16, int64_t D, const uint64_t* edge_keys,
+                                const int64_t* n_edges_dev, int64_t capacity, float* bsum, int32_t* bcnt,
+                                dm_stream_t stream) {
+    if (rows_own < 0 || W < 0 || ld < W || D <= 0 || capacity < 0) return DM_ERR_BAD_ARG;
+    if (rows_avail != rows_own && rows_avail != rows_own + 1) return DM_ERR_BAD_ARG;
+    if (rows_own == 0 || W == 0 || capacity == 0) return DM_OK;
+    if (!labels || !emb || !edge_keys || !n_edges_dev || !bsum || !bcnt) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    const unsigned g = pool::grid_for(rows_own * ceil_div(W, 32) * 32, 256, 8);
+    if (dtype_bf16) {
+        DM_COUNT_LAUNCH(); pool::pool_boundary_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(labels, rows_own, W, ld, rows_avail, (const __nv_bfloat16*)emb,
+                                                                        (int)D, edge_keys, n_edges_dev, bsum, bcnt);
+    } else {
+        DM_COUNT_LAUNCH(); pool::pool_boundary_kernel<float><<<g, 256, 0, s>>>(labels, rows_own, W, ld, rows_avail, (const float*)emb, (int)D,
+                                                                edge_keys, n_edges_dev, bsum, bcnt);
+    }
+    DM_LAUNCH_CHECK();
+    return DM_OK;
 }

@@ -225,6 +225,28 @@ def pool_dense(labels, emb, n_regions):
     return s, c
 
 
+def pool_boundary(labels, emb, edge_keys):
+    """Per-boundary pooling: for every 4-adjacent pixel pair straddling two regions, both pixels'
+    embeddings go to that edge -> (sum fp32 [E, D], cnt int32 [E] = 2 * boundary_len)."""
+    L = lib()
+    labels = _labels_2d(labels)
+    _need_cuda(labels, emb, edge_keys)
+    H, W = labels.shape
+    if emb.shape[:2] != labels.shape or emb.dtype not in (_F32, torch.bfloat16):
+        raise ValueError("emb must be float32 or bfloat16 [H, W, D]")
+    emb = emb.contiguous()
+    D = emb.shape[2]
+    E = edge_keys.shape[0]
+    dev = labels.device
+    s = torch.zeros((E, D), dtype=_F32, device=dev)
+    c = torch.zeros(E, dtype=_I32, device=dev)
+    with torch.cuda.device(dev):
+        n = torch.tensor([E], dtype=_I64, device=dev)
+        L.check(L.dm_pool_boundary(_p(labels), H, H, W, labels.stride(0), _p(emb), int(emb.dtype == torch.bfloat16), D,
+                                   _p(edge_keys.contiguous()), _p(n), E, _p(s), _p(c), _stream()), "dm_pool_boundary")
+    return s, c
+
+
 def score_l2(mean, edge_keys, norm2=None):
     """Euclidean distance between the pooled means of every edge's endpoints, the
     reference's formula (ExtractFeatures.py:139-147) -> fp32 [E]."""

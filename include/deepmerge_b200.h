@@ -159,6 +159,16 @@ int dm_region_mean(const float* sum, const int32_t* cnt, int64_t n_regions, int6
 int dm_pool_dense(const int32_t* labels, int64_t H, int64_t W, int64_t ld, const void* emb, int dtype_bf16,
                   int64_t D, int64_t n_regions, float* sum, int32_t* cnt, dm_stream_t stream);
 
+/* Per-boundary pooling of a dense embedding grid (north-star "per-boundary feature vectors"; the reference
+ * itself only writes one scalar per boundary, ExtractFeatures.py:217-219): for every 4-adjacent pixel pair
+ * with two different valid labels, both pixels' embeddings are ADDED to bsum[e] (fp32 [E, D]) of the edge e
+ * of that label pair and bcnt[e] (int32) grows by 2, so that mean = bsum / bcnt and bcnt = 2 * boundary_len.
+ * edge_keys must be the sorted unique list of dm_rag_build; pairs whose key is not in it are skipped.
+ * Row tiles: the tile owns pairs (y, y+1) for its rows y; emb must then hold rows_avail rows. */
+int dm_pool_boundary(const int32_t* labels, int64_t rows_own, int64_t rows_avail, int64_t W, int64_t ld,
+                     const void* emb, int dtype_bf16, int64_t D, const uint64_t* edge_keys,
+                     const int64_t* n_edges_dev, int64_t capacity, float* bsum, int32_t* bcnt, dm_stream_t stream);
+
 /* ----------------------------------------------------------------------------------- *
  * R6  Edge score = Euclidean distance between pooled means, the reference's expanded
  *     formula sqrt(max(0,|x|^2+|y|^2-2x.y)) in fp32 (ExtractFeatures.py:119-147, called

@@ -344,6 +344,24 @@ def pool_dense(labels, emb, n_regions):
     return s, cnt.astype(np.int64)
 
 
+def pool_boundary(labels, emb, keys):
+    """Per-boundary pooling (spec; no reference code: ExtractFeatures.py:217-219 only stores a scalar per
+    boundary): every 4-adjacent pixel pair with two different valid labels adds both pixels' embeddings to
+    the edge of that label pair.  -> (sum float64 [E, D], cnt int64 [E] = 2 * boundary_len)."""
+    L = np.asarray(labels, np.int64)
+    H, W = L.shape
+    D = emb.shape[-1]
+    E = np.asarray(emb, np.float64)
+    s = np.zeros((len(keys), D), np.float64)
+    c = np.zeros(len(keys), np.int64)
+    for a, b, ea, eb in ((L[:, :-1], L[:, 1:], E[:, :-1], E[:, 1:]), (L[:-1], L[1:], E[:-1], E[1:])):
+        m = (a != b) & (a >= 0) & (b >= 0)
+        idx = np.searchsorted(keys, pack_keys(a[m], b[m]))
+        np.add.at(s, idx, ea[m] + eb[m])
+        np.add.at(c, idx, 2)
+    return s, c
+
+
 # --------------------------------------------------------------------------- #
 # scoring
 # --------------------------------------------------------------------------- #

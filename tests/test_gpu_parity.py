@@ -401,3 +401,23 @@ def test_empty_inputs(cuda):
     assert relabel(torch.zeros((0, 4), dtype=torch.int32, device=cuda), torch.zeros(2, dtype=torch.int32, device=cuda)).numel() == 0
     with pytest.raises(ValueError):
         build_rag(torch.zeros((4, 4), dtype=torch.int32), 4)       # CPU tensor: no CPU path
+
+
+def test_pool_boundary_matches_oracle(cuda):
+    """Per-boundary pooling of a dense embedding grid: counts exact (= 2 * boundary_len), sums within 1e-3
+    relative of a float64 restatement (fp32 atomics, order not fixed)."""
+    import torch
+    from deepmerge_b200 import build_rag, pool_boundary
+    sc = o.synth_scene(96, 200, 150, C=0)
+    L, R = sc["labels"].copy(), sc["n_regions"]
+    L[5:9, 20:40] = -1
+    rng = np.random.default_rng(3)
+    for D, dt in ((100, torch.float32), (24, torch.bfloat16)):
+        emb = rng.standard_normal((96, 200, D)).astype(np.float32)
+        rag = build_rag(T(L, cuda), R)
+        emb_t = T(emb, cuda).to(dt)
+        s, c = pool_boundary(T(L, cuda), emb_t, rag.edge_keys)
+        ws, wc = o.pool_boundary(L, emb_t.float().cpu().numpy(), keys_np(rag.edge_keys))
+        assert np.array_equal(c.cpu().numpy(), wc)
+        assert np.array_equal(wc, 2 * rag.boundary_len.cpu().numpy().view(np.uint32).astype(np.int64))
+        np.testing.assert_allclose(s.cpu().numpy(), ws, rtol=1e-3, atol=1e-3)
