@@ -264,11 +264,27 @@ def b200_arm(args):
     res = step()
 
     # ---- end to end through the public API with HOST buffers -----------------------------------------
-    from deepmerge_b200 import merge_scene
+    # ScenePipeline: every step copies its inputs from pinned host memory and its label map back; the
+    # copies of neighbouring steps overlap the compute on separate streams (full-duplex PCIe).  The
+    # un-pipelined single call (merge_scene semantics) is reported next to it.
+    from deepmerge_b200 import ScenePipeline
     host = {k: getattr(sc, k).cpu().pin_memory() for k in ("labels", "image", "feats", "xs", "ys")}
-    out_host = torch.empty((H, W), dtype=torch.int32).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in host.values())
-    d2h = out_host.numel() * 4
+    d2h = H * W * 4
+    pipe = ScenePipeline(eng)
+    for _ in pipe.run((host for _ in range(3)), cfg["tau"]):
+        pass
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_out = 0
+    for lab in pipe.run((host for _ in range(args.steps)), cfg["tau"]):
+        n_out += 1
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    assert n_out == args.steps
+    eng.out = pipe.dev_out[0]
+
+    out_host = pipe.host_out[0]
 
     def e2e_step():
         d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
@@ -279,9 +295,9 @@ def b200_arm(args):
 
     e2e_step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(max(1, args.steps // 3)):
         e2e_step()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_single_ms = (time.perf_counter() - t0) * 1e3 / max(1, args.steps // 3)
 
     # ---- the pair-MLP scorer (R8) on the scene's edges: tcgen05 kernel timed alone ------------------------------
     mlp_rec = None
@@ -333,7 +349,8 @@ def b200_arm(args):
         "merged_edges_per_s": res.merges / (ms * 1e-3), "scored_edges_per_s": E0 / (ms * 1e-3),
         "segments_after": n_roots, "rounds": res.rounds,
         "e2e": {"value": H * W / e2e_ms / 1e3, "unit": "Mpx/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h},
+                "d2h_bytes_per_step": d2h, "api": "ScenePipeline.run (H2D / compute / D2H of neighbouring steps overlap)",
+                "unpipelined_ms_per_step": e2e_single_ms, "unpipelined_value": H * W / e2e_single_ms / 1e3},
         "gpu_launches": launches,
         "roofline": {"kernel": "rag_pool_kernel (fused RAG + band pooling raster pass)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,

@@ -554,6 +554,90 @@ class MergeEngine:
         return rounds, merges
 
 
+class ScenePipeline:
+    """Throughput mode for a stream of same-sized HOST scenes (the public API behind bench.py's `e2e`):
+    the pinned host -> device copy of scene k+1 and the device -> host copy of label map k-1 run on their
+    own CUDA streams while scene k computes, so a step costs max(H2D, D2H + compute) instead of their
+    sum (PCIe is full duplex).  Inputs and outputs are double buffered on the device; every scene still
+    pays its own H2D and D2H.
+
+        pipe = ScenePipeline(engine)
+        for labels_host in pipe.run(scenes, tau):      # scenes: iterable of dicts of pinned CPU tensors
+            ...                                        # labels_host: pinned int32 [H, W], valid until the
+                                                       # second-next iteration
+    """
+
+    KEYS = ("labels", "image", "feats", "xs", "ys")
+
+    def __init__(self, engine: "MergeEngine"):
+        self.eng = engine
+        dev = engine.dev
+        with torch.cuda.device(dev):
+            self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.dev_in = [None, None]
+        self.dev_out = [torch.empty((engine.H, engine.W), dtype=_I32, device=dev) for _ in range(2)]
+        self.host_out = [torch.empty((engine.H, engine.W), dtype=_I32).pin_memory() for _ in range(2)]
+        self.in_ready = [torch.cuda.Event() for _ in range(2)]
+        self.in_free = [None, None]          # compute finished with dev_in[i]
+        self.out_done = [None, None]         # D2H of dev_out[i] finished
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def _upload(self, i, scene):
+        """enqueue the H2D of one scene into input buffer i on the copy-in stream"""
+        dev = self.eng.dev
+        with torch.cuda.stream(self.s_in):
+            if self.in_free[i] is not None:
+                self.s_in.wait_event(self.in_free[i])
+            if self.dev_in[i] is None:
+                self.dev_in[i] = {k: torch.empty(scene[k].shape, dtype=scene[k].dtype, device=dev)
+                                  for k in self.KEYS if scene.get(k) is not None}
+            for k, d in self.dev_in[i].items():
+                d.copy_(scene[k], non_blocking=True)
+                self.h2d_bytes += d.numel() * d.element_size()
+            self.in_ready[i].record(self.s_in)
+
+    def run(self, scenes, tau, **kw):
+        eng = self.eng
+        cur = torch.cuda.current_stream(eng.dev)
+        it = iter(scenes)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        self._upload(0, nxt)
+        k = 0
+        pending = []                                         # (event, host buffer) of label maps on their way out
+        while nxt is not None:
+            i = k & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                self._upload(i ^ 1, nxt)                     # scene k+1 travels while scene k computes
+            cur.wait_event(self.in_ready[i])
+            if self.out_done[i] is not None:
+                cur.wait_event(self.out_done[i])             # label map k-2 has left dev_out[i]
+            d = self.dev_in[i]
+            eng.out = self.dev_out[i]
+            res = eng.run(d["labels"], d["feats"], tau, image=d.get("image"), xs=d.get("xs"), ys=d.get("ys"), **kw)
+            done = torch.cuda.Event()
+            done.record(cur)
+            self.in_free[i] = done
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(done)
+                self.host_out[i].copy_(res.labels, non_blocking=True)
+                self.d2h_bytes += res.labels.numel() * 4
+                ev = torch.cuda.Event()
+                ev.record(self.s_out)
+            self.out_done[i] = ev
+            pending.append((ev, self.host_out[i]))
+            if len(pending) > 1:                             # hand out label map k-1 once it has landed
+                e0, h0 = pending.pop(0)
+                e0.synchronize()
+                yield h0
+            k += 1
+        for e0, h0 in pending:
+            e0.synchronize()
+            yield h0
+
+
 def merge_graph(sum_, cnt, area, perimeter, edge_keys, boundary_len, tau, max_rounds=64, mlp=None):
     """Merge loop on an explicit region graph (spec SURVEY.md section 8(a) R9): edges with L2 score < tau
     are contracted, or -- when a PackedMLP is given -- edges whose pair-MLP logit 1 exceeds logit 0."""

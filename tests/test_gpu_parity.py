@@ -421,3 +421,22 @@ def test_pool_boundary_matches_oracle(cuda):
         assert np.array_equal(c.cpu().numpy(), wc)
         assert np.array_equal(wc, 2 * rag.boundary_len.cpu().numpy().view(np.uint32).astype(np.int64))
         np.testing.assert_allclose(s.cpu().numpy(), ws, rtol=1e-3, atol=1e-3)
+
+
+def test_scene_pipeline_equals_single_calls(cuda):
+    """ScenePipeline (overlapped H2D / compute / D2H over a stream of host scenes) returns, in order, exactly
+    the label maps of one-at-a-time calls."""
+    import torch
+    from deepmerge_b200 import MergeEngine, ScenePipeline
+    scenes, want = [], []
+    for seed in (1, 2, 3, 4, 5):
+        sc = o.synth_scene(128, 256, 200, C=4, seed=seed)
+        R = sc["n_regions"]
+        scenes.append({k: torch.from_numpy(np.ascontiguousarray(sc[k])).pin_memory() for k in ("labels", "image", "feats", "xs", "ys")})
+        want.append(o.merge_scene(sc["labels"], R, sc["region_of_point"], sc["feats"], tau=0.5)["labels"])
+    assert len({o.synth_scene(128, 256, 200, C=4, seed=s)["n_regions"] for s in (1, 2, 3, 4, 5)}) == 1
+    eng = MergeEngine(128, 256, R, 100, C=4, n_points=scenes[0]["feats"].shape[0], device=cuda)
+    got = [lab.clone().numpy() for lab in ScenePipeline(eng).run(iter(scenes), 0.5)]
+    assert len(got) == 5
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
