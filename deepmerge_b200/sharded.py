@@ -169,6 +169,10 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
     # weak scaling: N tiles of the single-GPU scene stacked vertically
     H, W, C, D, P = cfg["H"] * world, cfg["W"], cfg["C"], cfg["D"], cfg["P"]
     R_target = cfg["R"] * world
+    fixed_scene = bool(getattr(args, "config2", False))
+    if fixed_scene:                       # BASELINE.json configs[2]: ONE 40k x 40k scene split over the ranks (strong scaling)
+        cfg = dict(SHARDED_CFG)
+        H, W, C, D, P, R_target = cfg["H"], cfg["W"], cfg["C"], cfg["D"], cfg["P"], cfg["R"]
     y0, y1 = tile_bounds(H, world, rank)
     has_halo = rank < world - 1
     sc = synth_scene(H, W, R_target, C=C, P=P, D=D, seed=cfg["seed"], device=dev, rows=(y0, y1 + (1 if has_halo else 0)))
@@ -235,9 +239,11 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
         line = {
             "metric": "megapixels/sec end-to-end (RAG+pool+score+merge+relabel)", "value": H * W / ms / 1e3, "unit": "Mpx/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32/u8 index + fp32 scores", "data": "synthetic",
-            "config": {"workload": f"{workload1} -- one such tile per GPU, stacked by rows ({H}x{W}), row-tile sharded with "
-                                   "NCCL edge-list all-gather + region-statistics all-reduce",
+            "scaling": "strong" if fixed_scene else "weak", "vs_baseline": None, "dtype": "int32/u8 index + fp32 scores",
+            "data": "synthetic",
+            "config": {"workload": (SHARDED_WORKLOAD if fixed_scene else
+                                    f"{workload1} -- one such tile per GPU, stacked by rows ({H}x{W}), row-tile sharded with "
+                                    "NCCL edge-list all-gather + region-statistics all-reduce"),
                        "H": H, "W": W, "bands": C, "segments": R,
                        "points": int(sc.xs.shape[0]), "embed_dim": D, "tau": cfg["tau"], "parallelism": f"row-tiles x{world}",
                        "l2_policy": "inputs larger than L2, no flush needed"},
