@@ -75,7 +75,8 @@ __global__ void uf_compress_kernel(int32_t* __restrict__ parent, int64_t n) {
 __global__ void collect_members_kernel(const int32_t* __restrict__ parent, uint8_t* __restrict__ alive,
                                        uint8_t* __restrict__ changed, int32_t* __restrict__ cnt,
                                        unsigned long long* __restrict__ area, unsigned long long* __restrict__ perimeter,
-                                       int64_t R, uint64_t* __restrict__ list, unsigned long long* __restrict__ n_list) {
+                                       int64_t R, uint64_t* __restrict__ list, unsigned long long* __restrict__ n_list,
+                                       unsigned long long* __restrict__ n_moved, const uint8_t* __restrict__ root_mask) {
     for (int64_t x0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - (threadIdx.x & 31); x0 < R;
          x0 += (int64_t)gridDim.x * blockDim.x) {
         const int64_t x = x0 + (threadIdx.x & 31);
@@ -85,10 +86,16 @@ __global__ void collect_members_kernel(const int32_t* __restrict__ parent, uint8
             r = parent[x];
             moved = r != (int)x;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, moved);
-        if (!bal) continue;
+        const unsigned bal_moved = __ballot_sync(0xffffffffu, moved);
+        if (!bal_moved) continue;
+        // root_mask (row-tile sharding): only components this rank sees get their embedding sums merged here
+        const bool listed = moved && (!root_mask || root_mask[r]);
+        const unsigned bal = __ballot_sync(0xffffffffu, listed);
         unsigned long long base = 0;
-        if ((threadIdx.x & 31) == 0) base = atomicAdd(n_list, (unsigned long long)__popc(bal));
+        if ((threadIdx.x & 31) == 0) {
+            if (bal) base = atomicAdd(n_list, (unsigned long long)__popc(bal));
+            atomicAdd(n_moved, (unsigned long long)__popc(bal_moved));
+        }
         base = __shfl_sync(0xffffffffu, base, 0);
         if (moved) {
             alive[x] = 0;
@@ -96,7 +103,7 @@ __global__ void collect_members_kernel(const int32_t* __restrict__ parent, uint8
             atomicAdd(&cnt[r], cnt[x]);
             atomicAdd(&area[r], area[x]);
             atomicAdd(&perimeter[r], perimeter[x]);
-            list[base + __popc(bal & lanemask_lt())] = ((uint64_t)(unsigned)r << 32) | (unsigned)x;
+            if (listed) list[base + __popc(bal & lanemask_lt())] = ((uint64_t)(unsigned)r << 32) | (unsigned)x;
         }
     }
 }
@@ -249,11 +256,154 @@ __global__ void perimeter_edges_kernel(const uint64_t* __restrict__ keys, const 
     }
 }
 
+// ---- row-tile sharding helpers ------------------------------------------------------------------------
+__global__ void mark_endpoints_kernel(const uint64_t* __restrict__ keys, const int64_t* __restrict__ n_dev, int64_t R,
+                                      uint8_t* __restrict__ flags) {
+    const int64_t n = *n_dev;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = keys[e];
+        if (key_hi(k) < R) {
+            flags[key_lo(k)] = 1;
+            flags[key_hi(k)] = 1;
+        }
+    }
+}
+
+// one warp per region: flagged rows are appended (id, row) to the slot buffer; order inside the slot is arbitrary
+__global__ void __launch_bounds__(256) rows_pack_kernel(const uint8_t* __restrict__ flag, const float* __restrict__ rows,
+                                                        int64_t R, int D, int32_t* __restrict__ out_ids,
+                                                        float* __restrict__ out_rows, int64_t cap,
+                                                        unsigned long long* __restrict__ n_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r0 = warp0 * 32; r0 < R; r0 += nwarps * 32) {
+        const int64_t r = r0 + lane;
+        const bool f = r < R && flag[r];
+        unsigned m = __ballot_sync(0xffffffffu, f);
+        if (!m) continue;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        int j = 0;
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned long long slot = base + j++;
+            if ((long long)slot < cap) {                       // overflow is visible in the count
+                if (lane == 0) out_ids[slot] = (int32_t)(r0 + src);
+                for (int d = lane; d < D; d += 32) out_rows[slot * D + d] = rows[(r0 + src) * D + d];
+            }
+        }
+    }
+}
+
+// one warp per packed entry: rows[id] = row (add == 0) or rows[id] += row (add != 0; ids are distinct inside one slot)
+__global__ void __launch_bounds__(256) rows_unpack_kernel(const int32_t* __restrict__ ids, const float* __restrict__ in_rows,
+                                                          const int64_t* __restrict__ n_dev, int64_t cap, int64_t R, int D,
+                                                          float* __restrict__ rows, int add) {
+    const int64_t n = imin64(*n_dev, cap);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarps) {
+        const int64_t r = ids[i];
+        if (r < 0 || r >= R) continue;
+        for (int d = lane; d < D; d += 32) {
+            const float v = in_rows[i * D + d];
+            rows[r * D + d] = add ? rows[r * D + d] + v : v;
+        }
+    }
+}
+
+// rank-visibility masks: bit g of mask[r] = rank g sees region r.  A component is seen by every rank that sees a member.
+__global__ void shard_propagate_kernel(const int32_t* __restrict__ parent, const uint8_t* __restrict__ alive,
+                                       int32_t* __restrict__ mask, uint8_t* __restrict__ grew, int64_t R) {
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < R; x += (int64_t)gridDim.x * blockDim.x) {
+        const int p = parent[x];
+        if (alive[x] && p != (int)x) {
+            atomicOr(&mask[p], mask[x]);
+            grew[p] = 1;
+        }
+    }
+}
+// send[x]: this rank ships region x's embedding sum -- x belongs to a component that grew this round and is seen by
+// at least two ranks, and this rank is the lowest one that held x's sum before the round.
+__global__ void shard_plan_kernel(const int32_t* __restrict__ parent, const uint8_t* __restrict__ alive,
+                                  const int32_t* __restrict__ mask_old, const int32_t* __restrict__ mask_new,
+                                  const uint8_t* __restrict__ grew, int my_bit, int64_t R, uint8_t* __restrict__ send,
+                                  uint8_t* __restrict__ seen_comp) {
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < R; x += (int64_t)gridDim.x * blockDim.x) {
+        const int p = parent[x];
+        const int mo = mask_old[x], mp = mask_new[p];
+        seen_comp[x] = (mask_new[x] & my_bit) ? 1 : 0;
+        send[x] = (alive[x] && grew[p] && (mp & (mp - 1)) != 0 && (mo & -mo) == my_bit) ? 1 : 0;
+    }
+}
+
 }  // namespace merge
 }  // namespace dm
 
 using namespace dm;
 using merge::grid_for;
+
+extern "C" int dm_shard_propagate(const int32_t* parent, const uint8_t* alive, int32_t* mask, uint8_t* grew, int64_t n_regions,
+                                  dm_stream_t stream) {
+    if (n_regions < 0) return DM_ERR_BAD_ARG;
+    if (n_regions == 0) return DM_OK;
+    if (!parent || !alive || !mask || !grew) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    DM_CUDA(cudaMemsetAsync(grew, 0, (size_t)n_regions, s));
+    DM_COUNT_LAUNCH(); merge::shard_propagate_kernel<<<grid_for(n_regions), 256, 0, s>>>(parent, alive, mask, grew, n_regions);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_shard_plan(const int32_t* parent, const uint8_t* alive, const int32_t* mask_old, const int32_t* mask_new,
+                             const uint8_t* grew, int rank, int64_t n_regions, uint8_t* send, uint8_t* seen_comp,
+                             dm_stream_t stream) {
+    if (n_regions < 0 || rank < 0 || rank > 30) return DM_ERR_BAD_ARG;
+    if (n_regions == 0) return DM_OK;
+    if (!parent || !alive || !mask_old || !mask_new || !grew || !send || !seen_comp) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::shard_plan_kernel<<<grid_for(n_regions), 256, 0, S(stream)>>>(parent, alive, mask_old, mask_new, grew, 1 << rank,
+                                                                         n_regions, send, seen_comp);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_mark_endpoints(const uint64_t* edge_keys, const int64_t* n_edges_dev, int64_t capacity, int64_t n_regions,
+                                 uint8_t* flags, dm_stream_t stream) {
+    if (capacity < 0 || n_regions < 0) return DM_ERR_BAD_ARG;
+    if (capacity == 0 || n_regions == 0) return DM_OK;
+    if (!edge_keys || !n_edges_dev || !flags) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::mark_endpoints_kernel<<<grid_for(capacity), 256, 0, S(stream)>>>(edge_keys, n_edges_dev, n_regions, flags);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_rows_pack(const uint8_t* flag, const float* rows, int64_t n_regions, int64_t D, int32_t* out_ids,
+                            float* out_rows, int64_t capacity, int64_t* n_out_dev, dm_stream_t stream) {
+    if (n_regions < 0 || D <= 0 || capacity < 0 || !n_out_dev) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    DM_CUDA(cudaMemsetAsync(n_out_dev, 0, sizeof(int64_t), s));
+    if (n_regions == 0) return DM_OK;
+    if (!flag || !rows || (capacity > 0 && (!out_ids || !out_rows))) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::rows_pack_kernel<<<grid_for(n_regions), 256, 0, s>>>(flag, rows, n_regions, (int)D, out_ids, out_rows, capacity,
+                                                                (unsigned long long*)n_out_dev);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_rows_unpack(const int32_t* ids, const float* in_rows, const int64_t* n_dev, int64_t capacity,
+                              int64_t n_regions, int64_t D, float* rows, int add, dm_stream_t stream) {
+    if (n_regions < 0 || D <= 0 || capacity < 0) return DM_ERR_BAD_ARG;
+    if (capacity == 0 || n_regions == 0) return DM_OK;
+    if (!ids || !in_rows || !n_dev || !rows) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::rows_unpack_kernel<<<grid_for(capacity * 32), 256, 0, S(stream)>>>(ids, in_rows, n_dev, capacity, n_regions, (int)D,
+                                                                              rows, add);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
 
 extern "C" int dm_merge_select_l2(const float* scores, float tau, const int64_t* n_dev, int64_t capacity, uint8_t* selected,
                                   int64_t* n_sel, dm_stream_t stream) {
@@ -300,12 +450,14 @@ extern "C" int dm_uf_compress(int32_t* parent, int64_t R, dm_stream_t stream) {
 
 extern "C" size_t dm_merge_apply_workspace_bytes(int64_t R) {
     const int64_t cap = R < 1 ? 1 : R;
-    return align_up((size_t)cap * 8, 256) + prims::sort_ws_bytes(cap) + 256;
+    return align_up((size_t)cap * 8, 256) + prims::sort_ws_bytes(cap) + 512;
 }
 
-extern "C" int dm_merge_apply(const int32_t* parent, uint8_t* alive, uint8_t* changed, float* sum, int32_t* cnt,
-                              int64_t* area, int64_t* perimeter, int64_t R, int64_t D, int64_t* n_merged, void* ws,
-                              size_t ws_bytes, dm_stream_t stream) {
+extern "C" size_t dm_merge_apply_workspace_bytes(int64_t R);
+
+extern "C" int dm_merge_apply_masked(const int32_t* parent, uint8_t* alive, uint8_t* changed, float* sum, int32_t* cnt,
+                                     int64_t* area, int64_t* perimeter, int64_t R, int64_t D, int64_t* n_merged,
+                                     const uint8_t* root_mask, void* ws, size_t ws_bytes, dm_stream_t stream) {
     if (R < 0 || D <= 0 || !n_merged) return DM_ERR_BAD_ARG;
     cudaStream_t s = S(stream);
     DM_CUDA(cudaMemsetAsync(n_merged, 0, sizeof(int64_t), s));
@@ -315,15 +467,25 @@ extern "C" int dm_merge_apply(const int32_t* parent, uint8_t* alive, uint8_t* ch
     Carver c(ws);
     uint64_t* list = c.take<uint64_t>(R);
     void* sws = c.take<char>(prims::sort_ws_bytes(R));
+    int64_t* n_list = c.take<int64_t>(1);
     DM_CUDA(cudaMemsetAsync(changed, 0, (size_t)R, s));
+    DM_CUDA(cudaMemsetAsync(n_list, 0, sizeof(int64_t), s));
     DM_COUNT_LAUNCH(); merge::collect_members_kernel<<<grid_for(R), 256, 0, s>>>(parent, alive, changed, cnt, (unsigned long long*)area,
                                                               (unsigned long long*)perimeter, R, list,
-                                                              (unsigned long long*)n_merged);
+                                                              (unsigned long long*)n_list, (unsigned long long*)n_merged,
+                                                              root_mask);
     const int b = bits_for(R);
-    DM_TRY(prims::sort_pairs(list, nullptr, n_merged, R, b, 2 * b, sws, s));
-    DM_COUNT_LAUNCH(); merge::merge_sums_kernel<<<grid_for(R * 32), 256, 0, s>>>(list, n_merged, sum, (int)D);
+    DM_TRY(prims::sort_pairs(list, nullptr, n_list, R, b, 2 * b, sws, s));
+    DM_COUNT_LAUNCH(); merge::merge_sums_kernel<<<grid_for(R * 32), 256, 0, s>>>(list, n_list, sum, (int)D);
     DM_LAUNCH_CHECK();
     return DM_OK;
+}
+
+extern "C" int dm_merge_apply(const int32_t* parent, uint8_t* alive, uint8_t* changed, float* sum, int32_t* cnt,
+                              int64_t* area, int64_t* perimeter, int64_t R, int64_t D, int64_t* n_merged, void* ws,
+                              size_t ws_bytes, dm_stream_t stream) {
+    return dm_merge_apply_masked(parent, alive, changed, sum, cnt, area, perimeter, R, D, n_merged, nullptr, ws, ws_bytes,
+                                 stream);
 }
 
 extern "C" size_t dm_edges_rekey_workspace_bytes(int64_t capacity) {

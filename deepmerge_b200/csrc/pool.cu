@@ -28,16 +28,22 @@ __global__ void csr_keys_kernel(const int32_t* __restrict__ rop, int64_t n, int6
     }
 }
 
-// offsets[r] = first sorted position whose key >= r, for r in [0, R]
+// offsets[r] = first sorted position whose key >= r, for r in [0, R]: one binary search per region (region ids
+// with no points -- e.g. every region of the other row tiles -- cost the same as any other)
 __global__ void csr_offsets_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n,
                                    int64_t n_regions, int64_t* __restrict__ offsets, int32_t* __restrict__ point_ids) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t cur = i < n ? (int64_t)keys[i] : n_regions + 1;       // virtual terminator
-        const int64_t prev = i > 0 ? (int64_t)keys[i - 1] : -1;
-        const int64_t hi = cur < n_regions ? cur : n_regions;
-        for (int64_t r = prev + 1; r <= hi; ++r) offsets[r] = i;
-        if (i < n && cur < n_regions) point_ids[i] = (int32_t)vals[i];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t r = t0; r <= n_regions; r += stride) {
+        int64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((int64_t)keys[mid] < r) lo = mid + 1;
+            else hi = mid;
+        }
+        offsets[r] = lo;
     }
+    for (int64_t i = t0; i < n; i += stride)
+        if ((int64_t)keys[i] < n_regions) point_ids[i] = (int32_t)vals[i];
 }
 
 // One warp per region, lanes over the feature dimension, points visited in membership
@@ -260,7 +266,7 @@ extern "C" int dm_csr_build(const int32_t* rop, int64_t n, int64_t R, int64_t* o
     // stable sort by region only (input is in ascending point id): low bits_for(R+1) bits
     const int b = bits_for(R + 1);
     DM_TRY(prims::sort_pairs(keys, vals, n_dev, n, b, b, sws, s));
-    DM_COUNT_LAUNCH(); pool::csr_offsets_kernel<<<pool::grid_for(n + 1, 256, 8), 256, 0, s>>>(keys, vals, n, R, offsets, point_ids);
+    DM_COUNT_LAUNCH(); pool::csr_offsets_kernel<<<pool::grid_for((n > R ? n : R) + 1, 256, 8), 256, 0, s>>>(keys, vals, n, R, offsets, point_ids);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

@@ -392,11 +392,11 @@ class MergeEngine:
         z = lambda *s, dt: torch.zeros(*s, dtype=dt, device=dev)
         e = lambda *s, dt: torch.empty(*s, dtype=dt, device=dev)
         with torch.cuda.device(dev):
-            self.stats = z(2 * R + 2 * R * max(C, 1), dt=_I64)           # area | border | band_sum | band_sumsq
+            self.stats = z(3 * R + 2 * R * max(C, 1), dt=_I64)           # area | border | band_sum | band_sumsq | perimeter
             self.area, self.border = self.stats[:R], self.stats[R:2 * R]
             self.bsum = self.stats[2 * R:2 * R + R * C].view(R, C) if C else None
             self.bsq = self.stats[2 * R + R * max(C, 1):2 * R + R * max(C, 1) + R * C].view(R, C) if C else None
-            self.perim = e(R, dt=_I64)
+            self.perim = self.stats[2 * R + 2 * R * max(C, 1):]          # (one buffer -> one all-reduce when sharded)
             self.keys, self.blen, self.scores = e(cap, dt=_I64), e(cap, dt=_I32), e(cap, dt=_F32)
             self.selected = e(cap, dt=_U8)
             self.counts = z(8, dt=_I64)       # [0..3] rag counts, [4] n_selected, [5] n_merged

@@ -2,21 +2,27 @@
 
 Rank g owns rows [g*H/G, (g+1)*H/G) of labels / image plus ONE halo row below: the vertical
 pixel pair (y, y+1) belongs to the tile that owns y, so nothing is counted twice.  Region ids
-are global.  One exchange step per phase, with torch.distributed as plumbing (NCCL on the
-GPUs; the same code runs under gloo on CPU tensors, which is how the host logic is tested):
+are global.  torch.distributed is the plumbing (NCCL on the GPUs; the same code runs against the
+in-process stand-in of the tests).
 
-  1. per-tile unique (key, boundary_len) lists: all_gather_into_tensor of fixed-capacity slots plus
-     the device-side counts -> dm_edges_concat + dm_edges_sort_unique merge them into the global
-     edge list on every rank (replicated); no length ever travels to the host;
-  2. per-region partial statistics: all_reduce(sum) of [area | border | band sums | band
-     sums of squares] (int64) and of the pooled embedding sums / point counts;
-  3. graph-level work (scoring, union-find merge loop) is small and runs replicated and
-     deterministic on every rank -- no further collectives;
-  4. the final relabel is tile-local with the replicated root LUT.
+`ShardedMergeEngine.run` -- distributed merge loop, no rank ever holds the whole graph:
+  * every rank keeps ITS TILE's edge list (the edges physically inside the tile) and scores,
+    selects, re-keys and uniques only those;
+  * per-region small state is replicated: the parent array (int32 [R]), point counts, the alive /
+    changed flags and a rank-visibility bit mask (bit g = rank g sees the region: it has pixels
+    or an edge of it).  Each round the local unions are merged with all_reduce(min) of the
+    parent array + re-union until nothing changes;
+  * embedding sums [R, D] are NOT replicated: a rank holds the rows of the regions it sees.  Rows
+    travel sparsely: once for the regions seen by two ranks (their per-tile partial sums are
+    added in rank order), and per round for the members of components that grew across a tile
+    border (shipped by the lowest rank that held the row), as fixed-capacity slots with
+    device-side counts (dm_rows_pack / all_gather_into_tensor / dm_rows_unpack);
+  * area / border / perimeter / band sums stay per-tile partials through the loop (every update
+    is linear) and are all-reduced once at the end together with the gathered final edge list.
+Integer outputs are bit-identical to the single-GPU result; the fp32 sums of regions whose points
+lie in two tiles are added in rank order instead of point order (last-bit differences).
 
-The pooled fp32 sums of a region that spans tiles are reduced in NCCL's order, not in the
-reference's point order, so they can differ from the single-GPU result in the last bits;
-integer outputs are identical and merge decisions agree outside the stated guard band.
+`ShardedMergeEngine.run_replicated` is the earlier scheme (global graph replicated on every rank).
 """
 from __future__ import annotations
 
@@ -86,11 +92,13 @@ class ShardedMergeEngine:
     travel as fixed-capacity slots together with their device-side counts, and overflow / bad-label
     flags of the tile pass are checked with that first read-back."""
 
-    def __init__(self, H, W, n_regions, D, C, n_points_local, dist, device, group=None, slot_capacity=None):
+    def __init__(self, H, W, n_regions, D, C, n_points_local, dist, device, group=None, slot_capacity=None,
+                 row_capacity=None):
         from .raster import MergeEngine, default_edge_capacity
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.H, self.W = H, W
+        self.row_capacity = row_capacity
         self.y0, self.y1 = tile_bounds(H, self.world, self.rank)
         self.rows_own = self.y1 - self.y0
         self.has_halo = self.rank < self.world - 1
@@ -103,7 +111,174 @@ class ShardedMergeEngine:
         self.tile_counts = torch.zeros(4, dtype=torch.int64, device=dev)
         self.cat_counts = torch.zeros(2, dtype=torch.int64, device=dev)
 
-    def run(self, labels_tile, feats_local, tau, *, image_tile=None, xs_local=None, ys_local_rel=None, max_rounds=64):
+    # ------------------------------------------------------------------------------------------------
+    # distributed merge loop
+    # ------------------------------------------------------------------------------------------------
+    def _alloc_dist(self):
+        e = self.eng
+        dev, R, D = e.dev, e.R, e.D
+        # frontier / cross-component rows per rank and exchange (overflow is detected and reported)
+        self.row_cap = int(self.row_capacity) if self.row_capacity else int(min(R, max(4096, self.W // 2)))
+        z = lambda *sh, dt: torch.zeros(*sh, dtype=dt, device=dev)
+        self.seen, self.grew, self.send, self.seen_comp = (z(R, dt=torch.uint8) for _ in range(4))
+        self.mask_old = z(R, dt=torch.int32)
+        self.cnt_local = z(R, dt=torch.int32)
+        self.mask_cnt = z(2 * R, dt=torch.int32)                   # [mask | cnt]: one all-reduce
+        self.mask = self.mask_cnt[:R]
+        self.agreed = z(R, dt=torch.int32)
+        # one exchange slot = [count (16 B) | ids | rows] in ONE byte buffer: a single all_gather per exchange
+        self.slot_bytes = 16 + 4 * self.row_cap + 4 * self.row_cap * D
+        self.slot_bytes += (-self.slot_bytes) % 16
+        self.slot = z(self.slot_bytes, dt=torch.uint8)
+        self.slot_n = self.slot[:8].view(torch.int64)
+        self.slot_ids = self.slot[16:16 + 4 * self.row_cap].view(torch.int32)
+        self.slot_rows = self.slot[16 + 4 * self.row_cap:16 + 4 * self.row_cap * (D + 1)].view(torch.float32).view(self.row_cap, D)
+        self.zero_rows = z((self.row_cap, D), dt=torch.float32)
+        # final edge-list gather: [count (16 B) | keys | lens]
+        self.eslot_bytes = 16 + 12 * self.slot_cap
+        self.eslot_bytes += (-self.eslot_bytes) % 16
+        self.eslot = z(self.eslot_bytes, dt=torch.uint8)
+        self.flags = z(4, dt=torch.int64)                          # [0] selected (global), [1] parent changed, [2] slot overflow
+        self.host_flags = torch.zeros(4, dtype=torch.int64).pin_memory()
+
+    def _exchange_rows(self, flag, add):
+        """Ship the embedding sums of the flagged regions to every rank: pack -> all_gather (fixed slots + device
+        counts) -> unpack slot by slot in rank order (add: partial sums are accumulated in that order)."""
+        from .raster import _p, _stream
+        e, L, dist, s = self.eng, self.eng.L, self.dist, _stream()
+        L.check(L.dm_rows_pack(_p(flag), _p(e.sum), e.R, e.D, _p(self.slot_ids), _p(self.slot_rows), self.row_cap,
+                               _p(self.slot_n), s), "dm_rows_pack")
+        self.flags[2:3].copy_(torch.maximum(self.flags[2:3], (self.slot_n > self.row_cap).to(torch.int64)))
+        g = all_gather_slots(self.slot, dist, self.group).view(self.world, self.slot_bytes)
+        rc = self.row_cap
+        g_n = [g[r, :8].view(torch.int64) for r in range(self.world)]
+        g_ids = [g[r, 16:16 + 4 * rc].view(torch.int32) for r in range(self.world)]
+        g_rows = [g[r, 16 + 4 * rc:16 + 4 * rc * (e.D + 1)].view(torch.float32) for r in range(self.world)]
+        if add:                                                    # start from zero for every row that receives a partial
+            for g in range(self.world):
+                L.check(L.dm_rows_unpack(_p(g_ids[g]), _p(self.zero_rows), _p(g_n[g]), self.row_cap, e.R, e.D,
+                                         _p(e.sum), 0, s), "dm_rows_unpack")
+        for g in range(self.world):
+            L.check(L.dm_rows_unpack(_p(g_ids[g]), _p(g_rows[g]), _p(g_n[g]), self.row_cap, e.R, e.D,
+                                     _p(e.sum), int(add), s), "dm_rows_unpack")
+
+    def _read_flags(self):
+        e = self.eng
+        self.host_flags.copy_(self.flags, non_blocking=True)
+        e.host_counts.copy_(e.counts, non_blocking=True)
+        e.done.record()
+        e.done.synchronize()
+        return self.host_flags.tolist(), e.host_counts.tolist()
+
+    def run(self, labels_tile, feats_local, tau, *, image_tile=None, xs_local=None, ys_local_rel=None, max_rounds=64,
+            gather_outputs=True):
+        """labels_tile: int32 [rows_own (+1 halo), W]; ys_local_rel are rows relative to the tile.
+        gather_outputs: all-reduce the per-tile statistics and gather the final edge list (MergeResult as on one GPU)."""
+        from .raster import MergeResult, _p, _stream
+        e, L, dist, grp = self.eng, self.eng.L, self.dist, self.group
+        R, D, cap = e.R, e.D, e.cap
+        if not hasattr(self, "mask"):
+            self._alloc_dist()
+        MIN, MAX, SUM = dist.ReduceOp.MIN, dist.ReduceOp.MAX, dist.ReduceOp.SUM
+        with torch.cuda.device(e.dev):
+            s = _stream()
+            n_edges = e.counts[0:1]
+            # (1) tile pass: fused RAG + band pooling; e.keys / e.blen = the tile's own edge list,
+            #     e.perim = border + incident boundary lengths of THIS tile (a partial, like area and the band sums)
+            e._rag(labels_tile, image_tile, self.rows_own, self.rank == 0, self.rank == self.world - 1)
+            # (2) which ranks see which region
+            self.seen.copy_(e.area > 0)
+            L.check(L.dm_mark_endpoints(_p(e.keys), _p(n_edges), cap, R, _p(self.seen), s), "dm_mark_endpoints")
+            torch.mul(self.seen, 1 << self.rank, out=self.mask)
+            # (3) pooled embeddings: per-tile partial sums; counts replicated, rows of regions seen by two ranks exchanged
+            e._pool(labels_tile, xs_local, ys_local_rel, None, feats_local)
+            self.cnt_local.copy_(e.cnt)
+            self.mask_cnt[R:].copy_(e.cnt)
+            dist.all_reduce(self.mask_cnt, op=SUM, group=grp)       # masks: distinct bits, the sum is the OR
+            e.cnt.copy_(self.mask_cnt[R:])
+            self.flags.zero_()
+            frontier = (self.mask & (self.mask - 1)) != 0
+            self.send.copy_(frontier & (self.cnt_local > 0))
+            self._exchange_rows(self.send, add=True)
+            # (4) merge loop on the tile's edges with the replicated parent array
+            e.parent.copy_(e.iota)
+            e.alive.fill_(1)
+            e.counts[5:8].zero_()
+            L.check(L.dm_region_mean(_p(e.sum), _p(e.cnt), R, D, _p(e.mean), _p(e.norm2), _p(self.seen), s), "dm_region_mean")
+            L.check(L.dm_score_l2(_p(e.mean), _p(e.norm2), D, _p(e.keys), _p(n_edges), cap, None, _p(e.scores), s), "dm_score_l2")
+            rounds = merges = 0
+            while True:
+                L.check(L.dm_merge_select_l2(_p(e.scores), float(tau), _p(n_edges), cap, _p(e.selected),
+                                             e.counts[4:5].data_ptr(), s), "dm_merge_select_l2")
+                self.flags[0:1].copy_(e.counts[4:5])
+                dist.all_reduce(self.flags[0:1], op=SUM, group=grp)
+                f, c = self._read_flags()
+                if rounds == 0:
+                    if c[3] == 1:
+                        raise ValueError("labels contain ids >= n_regions")
+                    if c[3] != 0 or c[2] != 0:
+                        raise RuntimeError("tile edge list overflow / pipeline error (capacity %d, needed %d)" % (cap, c[1]))
+                if f[2] != 0:
+                    raise RuntimeError("row exchange slot overflow (row_cap %d)" % self.row_cap)
+                merges += int(c[5])
+                if f[0] == 0 or rounds == max_rounds:
+                    break
+                rounds += 1
+                # union-find: local unions, then all_reduce(min) + re-union until every rank holds the same forest
+                L.check(L.dm_uf_union(_p(e.parent), _p(e.keys), _p(e.selected), _p(n_edges), cap, s), "dm_uf_union")
+                L.check(L.dm_uf_compress(_p(e.parent), R, s), "dm_uf_compress")
+                while True:
+                    # two merge iterations per convergence check (one host round trip instead of two in the usual case)
+                    for _ in range(2):
+                        dist.all_reduce(e.parent, op=MIN, group=grp)
+                        self.agreed.copy_(e.parent)
+                        L.check(L.dm_uf_union(_p(e.parent), _p(e.keys), _p(e.selected), _p(n_edges), cap, s), "dm_uf_union")
+                        L.check(L.dm_uf_compress(_p(e.parent), R, s), "dm_uf_compress")
+                    self.flags[1:2].copy_((e.parent != self.agreed).any().to(torch.int64))
+                    dist.all_reduce(self.flags[1:2], op=MAX, group=grp)
+                    if int(self.flags[1].item()) == 0:
+                        break
+                # rows of components that grew across a tile border go to every rank that now sees them
+                self.mask_old.copy_(self.mask)
+                L.check(L.dm_shard_propagate(_p(e.parent), _p(e.alive), _p(self.mask), _p(self.grew), R, s), "dm_shard_propagate")
+                L.check(L.dm_shard_plan(_p(e.parent), _p(e.alive), _p(self.mask_old), _p(self.mask), _p(self.grew), self.rank, R,
+                                        _p(self.send), _p(self.seen_comp), s), "dm_shard_plan")
+                self._exchange_rows(self.send, add=False)
+                L.check(L.dm_merge_apply_masked(_p(e.parent), _p(e.alive), _p(e.changed), _p(e.sum), _p(e.cnt), _p(e.area),
+                                                _p(e.perim), R, D, e.counts[5:6].data_ptr(), _p(self.seen_comp), _p(e.ws),
+                                                e.ws_bytes, s), "dm_merge_apply_masked")
+                L.check(L.dm_edges_rekey(_p(e.parent), _p(e.keys), _p(e.blen), _p(e.scores), _p(n_edges), cap, R, _p(e.perim),
+                                         _p(e.ws), e.ws_bytes, s), "dm_edges_rekey")
+                L.check(L.dm_region_mean(_p(e.sum), _p(e.cnt), R, D, _p(e.mean), _p(e.norm2), _p(e.changed), s), "dm_region_mean")
+                L.check(L.dm_score_l2(_p(e.mean), _p(e.norm2), D, _p(e.keys), _p(n_edges), cap, _p(e.changed), _p(e.scores), s),
+                        "dm_score_l2")
+            # (5) tile-local relabel with the replicated root LUT
+            L.check(L.dm_relabel(_p(labels_tile), self.rows_own, self.W, labels_tile.stride(0), _p(e.parent), R, _p(e.out),
+                                 self.W, s), "dm_relabel")
+            Ef = int(e.host_counts[0])
+            if gather_outputs:
+                # per-tile partials -> global statistics; tile edge lists -> the global final edge list
+                allreduce_sum_(e.stats, dist, grp)                  # area | border | band sums | perimeter in one buffer
+                sc_ = self.slot_cap
+                self.eslot[:8].view(torch.int64).copy_(e.counts[0:1])
+                self.eslot[16:16 + 8 * sc_].view(torch.int64).copy_(e.keys[:sc_])
+                self.eslot[16 + 8 * sc_:16 + 12 * sc_].view(torch.int32).copy_(e.blen[:sc_])
+                ge = all_gather_slots(self.eslot, dist, grp).view(self.world, self.eslot_bytes)
+                gc = torch.stack([ge[r, :8].view(torch.int64)[0] for r in range(self.world)])
+                gk = torch.cat([ge[r, 16:16 + 8 * sc_].view(torch.int64) for r in range(self.world)])
+                gl = torch.cat([ge[r, 16 + 8 * sc_:16 + 12 * sc_].view(torch.int32) for r in range(self.world)])
+                L.check(L.dm_edges_concat(_p(gk), _p(gl), _p(gc), self.world, sc_, _p(e.keys), _p(e.blen), cap,
+                                          _p(self.cat_counts), s), "dm_edges_concat")
+                L.check(L.dm_edges_sort_unique(_p(e.keys), _p(e.blen), _p(self.cat_counts), cap, R, _p(e.counts), _p(e.ws),
+                                               e.ws_bytes, s), "dm_edges_sort_unique")
+                cc = torch.cat([e.counts[0:1], self.cat_counts[1:2]]).tolist()
+                if cc[1] != 0:
+                    raise RuntimeError("final edge list gather overflow (slot %d)" % self.slot_cap)
+                Ef = int(cc[0])
+        return MergeResult(e.out[: self.rows_own], e.parent, rounds, merges, e.keys[:Ef], e.blen[:Ef], None, e.area,
+                           e.perim, e.sum, e.cnt)
+
+    def run_replicated(self, labels_tile, feats_local, tau, *, image_tile=None, xs_local=None, ys_local_rel=None, max_rounds=64):
         """labels_tile: int32 [rows_own (+1 halo), W]; ys_local_rel are rows relative to the tile."""
         from .raster import MergeResult, _p, _stream
         e, L, dist = self.eng, self.eng.L, self.dist

@@ -231,6 +231,11 @@ size_t dm_merge_apply_workspace_bytes(int64_t n_regions);
 int dm_merge_apply(const int32_t* parent, uint8_t* alive, uint8_t* changed, float* sum, int32_t* cnt,
                    int64_t* area, int64_t* perimeter, int64_t n_regions, int64_t D, int64_t* n_merged_dev,
                    void* ws, size_t ws_bytes, dm_stream_t stream);
+/* dm_merge_apply restricted for row-tile sharding: counts / areas / perimeters of every absorbed region are merged,
+ * but embedding sums only for components whose root has root_mask[root] != 0 (nullable = all). */
+int dm_merge_apply_masked(const int32_t* parent, uint8_t* alive, uint8_t* changed, float* sum, int32_t* cnt,
+                          int64_t* area, int64_t* perimeter, int64_t n_regions, int64_t D, int64_t* n_merged_dev,
+                          const uint8_t* root_mask, void* ws, size_t ws_bytes, dm_stream_t stream);
 size_t dm_edges_rekey_workspace_bytes(int64_t capacity);
 int dm_edges_rekey(const int32_t* parent, uint64_t* edge_keys, uint32_t* boundary_len, float* scores,
                    int64_t* n_edges_dev, int64_t capacity, int64_t n_regions, int64_t* perimeter,
@@ -241,6 +246,29 @@ int dm_relabel(const int32_t* labels, int64_t H, int64_t W, int64_t ld_in, const
 size_t dm_compact_roots_workspace_bytes(int64_t n_regions);
 int dm_compact_roots(const int32_t* root, int64_t n_regions, int32_t* compact, int64_t* n_roots_dev,
                      void* ws, size_t ws_bytes, dm_stream_t stream);
+
+/* ----------------------------------------------------------------------------------- *
+ * Row-tile sharding helpers: the sparse exchanges of the owner-free
+ * distributed merge loop (deepmerge_b200/sharded.py).
+ * dm_mark_endpoints: flags[lo] = flags[hi] = 1 for every edge of the list (regions this tile sees).
+ * dm_rows_pack:  rows of the regions with flag[r] != 0 -> (out_ids, out_rows) in arbitrary order;
+ *                n_out_dev[0] = number of flagged regions (> capacity: the slot overflowed).
+ * dm_rows_unpack: rows[ids[i]] = in_rows[i] (add == 0) or += (add != 0); ids distinct within a call.
+ * ----------------------------------------------------------------------------------- */
+ /* dm_shard_propagate: mask[root] |= mask[x] for every region absorbed this round (bit g = rank g sees it);
+ *                     grew[root] = 1.   dm_shard_plan: send[x] = this rank ships x's embedding sum (see sharded.py),
+ *                     seen_comp[r] = this rank sees component r. */
+int dm_shard_propagate(const int32_t* parent, const uint8_t* alive, int32_t* mask, uint8_t* grew, int64_t n_regions,
+                       dm_stream_t stream);
+int dm_shard_plan(const int32_t* parent, const uint8_t* alive, const int32_t* mask_old, const int32_t* mask_new,
+                  const uint8_t* grew, int rank, int64_t n_regions, uint8_t* send, uint8_t* seen_comp,
+                  dm_stream_t stream);
+int dm_mark_endpoints(const uint64_t* edge_keys, const int64_t* n_edges_dev, int64_t capacity, int64_t n_regions,
+                      uint8_t* flags, dm_stream_t stream);
+int dm_rows_pack(const uint8_t* flag, const float* rows, int64_t n_regions, int64_t D, int32_t* out_ids,
+                 float* out_rows, int64_t capacity, int64_t* n_out_dev, dm_stream_t stream);
+int dm_rows_unpack(const int32_t* ids, const float* in_rows, const int64_t* n_dev, int64_t capacity,
+                   int64_t n_regions, int64_t D, float* rows, int add, dm_stream_t stream);
 
 /* ----------------------------------------------------------------------------------- *
  * R11 Contrastive pair loss forward + backward (Losses.py:34-38):

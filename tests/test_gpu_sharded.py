@@ -15,7 +15,7 @@ class FakeDist:
     """Minimal torch.distributed look-alike for `world` threads in one process."""
 
     class ReduceOp:
-        SUM, MAX = "sum", "max"
+        SUM, MAX, MIN = "sum", "max", "min"
 
     def __init__(self, world):
         import torch
@@ -46,18 +46,19 @@ class FakeDist:
         vals = self._exchange(t)
         acc = vals[0].clone()
         for v in vals[1:]:                      # fixed rank order
-            acc = acc + v if op == "sum" else self.torch.maximum(acc, v)
+            acc = acc + v if op == "sum" else (self.torch.maximum(acc, v) if op == "max" else self.torch.minimum(acc, v))
         t.copy_(acc)
 
 
-@pytest.mark.parametrize("world,H,W,R", [(2, 260, 384, 500), (3, 301, 640, 1500)])
-def test_sharded_equals_single_gpu_and_oracle(cuda, world, H, W, R):
+@pytest.mark.parametrize("world,H,W,R,tau", [(2, 260, 384, 500, 0.5), (3, 301, 640, 1500, 0.5), (4, 203, 512, 900, 0.5),
+                                              (4, 64, 256, 700, 0.5), (3, 240, 384, 600, 30.0)])
+def test_sharded_equals_single_gpu_and_oracle(cuda, world, H, W, R, tau):
     import torch
     from deepmerge_b200 import merge_scene
     from deepmerge_b200.sharded import ShardedMergeEngine, points_in_tile, tile_bounds
     sc = o.synth_scene(H, W, R, C=4)
     n, D = sc["n_regions"], sc["feats"].shape[1]
-    want = o.merge_scene(sc["labels"], n, sc["region_of_point"], sc["feats"], tau=0.5)
+    want = o.merge_scene(sc["labels"], n, sc["region_of_point"], sc["feats"], tau=tau)
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
     fd = FakeDist(world)
     results, errors = [None] * world, []
@@ -72,7 +73,7 @@ def test_sharded_equals_single_gpu_and_oracle(cuda, world, H, W, R):
             image = T(sc["image"][y0:y1])
             mine = points_in_tile(torch.from_numpy(sc["ys"]), y0, y1).numpy()
             eng = ShardedMergeEngine(H, W, n, D, 4, len(mine), fd, cuda)
-            res = eng.run(labels, T(sc["feats"][mine]), 0.5, image_tile=image, xs_local=T(sc["xs"][mine]),
+            res = eng.run(labels, T(sc["feats"][mine]), tau, image_tile=image, xs_local=T(sc["xs"][mine]),
                           ys_local_rel=T(sc["ys"][mine] - y0))
             torch.cuda.synchronize()
             results[rank] = (res.labels.cpu().numpy(), res.root.cpu().numpy(), res.rounds, res.merges,
@@ -95,5 +96,5 @@ def test_sharded_equals_single_gpu_and_oracle(cuda, world, H, W, R):
         assert np.array_equal(r[4][roots], want["area"][roots]) and np.array_equal(r[5][roots], want["perim"][roots])
         assert np.array_equal(r[6], want["keys"])
         assert np.array_equal(r[7], s)                                # band sums: integer all-reduce, exact
-    single = merge_scene(T(sc["labels"]), T(sc["feats"]), 0.5, n_regions=n, image=T(sc["image"]), xs=T(sc["xs"]), ys=T(sc["ys"]))
+    single = merge_scene(T(sc["labels"]), T(sc["feats"]), tau, n_regions=n, image=T(sc["image"]), xs=T(sc["xs"]), ys=T(sc["ys"]))
     assert np.array_equal(single.labels.cpu().numpy(), full)
