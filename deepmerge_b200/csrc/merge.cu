@@ -341,11 +341,44 @@ __global__ void shard_plan_kernel(const int32_t* __restrict__ parent, const uint
     }
 }
 
+// All slots of an all-gathered exchange buffer in one launch.  Slot layout: int64 count | pad to 16 B | int32 ids[cap] |
+// float rows[cap][D].  zero != 0 writes zeros (ids may repeat across slots: benign), else copies (ids distinct overall).
+__global__ void __launch_bounds__(256) rows_unpack_slots_kernel(const unsigned char* __restrict__ buf, int n_slots,
+                                                                int64_t slot_bytes, int64_t cap, int64_t R, int D,
+                                                                float* __restrict__ rows, int zero) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = warp0; w < (int64_t)n_slots * cap; w += nwarps) {
+        const int g = (int)(w / cap);
+        const int64_t i = w - (int64_t)g * cap;
+        const unsigned char* slot = buf + (size_t)g * slot_bytes;
+        if (i >= *(const int64_t*)slot) continue;
+        const int64_t r = ((const int32_t*)(slot + 16))[i];
+        if (r < 0 || r >= R) continue;
+        const float* src = (const float*)(slot + 16 + 4 * cap) + i * D;
+        for (int d = lane; d < D; d += 32) rows[r * D + d] = zero ? 0.f : src[d];
+    }
+}
+
 }  // namespace merge
 }  // namespace dm
 
 using namespace dm;
 using merge::grid_for;
+
+extern "C" int dm_rows_unpack_slots(const void* slots, int64_t n_slots, int64_t slot_bytes, int64_t slot_capacity,
+                                    int64_t n_regions, int64_t D, float* rows, int zero, dm_stream_t stream) {
+    if (n_slots < 0 || slot_capacity < 0 || n_regions < 0 || D <= 0 || slot_bytes < 16 + 4 * slot_capacity * (D + 1) ||
+        (slot_bytes & 15))
+        return DM_ERR_BAD_ARG;
+    if (n_slots == 0 || slot_capacity == 0 || n_regions == 0) return DM_OK;
+    if (!slots || !rows) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::rows_unpack_slots_kernel<<<grid_for(n_slots * slot_capacity * 32), 256, 0, S(stream)>>>(
+        (const unsigned char*)slots, (int)n_slots, slot_bytes, slot_capacity, n_regions, (int)D, rows, zero);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
 
 extern "C" int dm_shard_propagate(const int32_t* parent, const uint8_t* alive, int32_t* mask, uint8_t* grew, int64_t n_regions,
                                   dm_stream_t stream) {

@@ -133,7 +133,6 @@ class ShardedMergeEngine:
         self.slot_n = self.slot[:8].view(torch.int64)
         self.slot_ids = self.slot[16:16 + 4 * self.row_cap].view(torch.int32)
         self.slot_rows = self.slot[16 + 4 * self.row_cap:16 + 4 * self.row_cap * (D + 1)].view(torch.float32).view(self.row_cap, D)
-        self.zero_rows = z((self.row_cap, D), dt=torch.float32)
         # final edge-list gather: [count (16 B) | keys | lens]
         self.eslot_bytes = 16 + 12 * self.slot_cap
         self.eslot_bytes += (-self.eslot_bytes) % 16
@@ -154,13 +153,13 @@ class ShardedMergeEngine:
         g_n = [g[r, :8].view(torch.int64) for r in range(self.world)]
         g_ids = [g[r, 16:16 + 4 * rc].view(torch.int32) for r in range(self.world)]
         g_rows = [g[r, 16 + 4 * rc:16 + 4 * rc * (e.D + 1)].view(torch.float32) for r in range(self.world)]
-        if add:                                                    # start from zero for every row that receives a partial
-            for g in range(self.world):
-                L.check(L.dm_rows_unpack(_p(g_ids[g]), _p(self.zero_rows), _p(g_n[g]), self.row_cap, e.R, e.D,
-                                         _p(e.sum), 0, s), "dm_rows_unpack")
-        for g in range(self.world):
-            L.check(L.dm_rows_unpack(_p(g_ids[g]), _p(g_rows[g]), _p(g_n[g]), self.row_cap, e.R, e.D,
-                                     _p(e.sum), int(add), s), "dm_rows_unpack")
+        if add:       # partial sums: clear every row that receives one, then add slot by slot (= in rank order)
+            L.check(L.dm_rows_unpack_slots(_p(g), self.world, self.slot_bytes, rc, e.R, e.D, _p(e.sum), 1, s), "dm_rows_unpack_slots")
+            for r in range(self.world):
+                L.check(L.dm_rows_unpack(_p(g_ids[r]), _p(g_rows[r]), _p(g_n[r]), rc, e.R, e.D, _p(e.sum), 1, s),
+                        "dm_rows_unpack")
+        else:         # whole rows from their single sender: one launch for all slots
+            L.check(L.dm_rows_unpack_slots(_p(g), self.world, self.slot_bytes, rc, e.R, e.D, _p(e.sum), 0, s), "dm_rows_unpack_slots")
 
     def _read_flags(self):
         e = self.eng
@@ -173,7 +172,12 @@ class ShardedMergeEngine:
     def run(self, labels_tile, feats_local, tau, *, image_tile=None, xs_local=None, ys_local_rel=None, max_rounds=64,
             gather_outputs=True):
         """labels_tile: int32 [rows_own (+1 halo), W]; ys_local_rel are rows relative to the tile.
-        gather_outputs: all-reduce the per-tile statistics and gather the final edge list (MergeResult as on one GPU)."""
+
+        The result is DISTRIBUTED unless gather_outputs: labels = this tile's label map, root / cnt replicated,
+        edge_keys / boundary_len = this tile's final edge list (the global list is the union, lengths add up),
+        area / perimeter (and the engine's band sums) = this tile's partials (they add up over ranks), sum = rows of
+        the regions this rank sees.  gather_outputs=True all-reduces the statistics and gathers + uniques the edge
+        lists so that every rank holds the same MergeResult a single GPU would produce."""
         from .raster import MergeResult, _p, _stream
         e, L, dist, grp = self.eng, self.eng.L, self.dist, self.group
         R, D, cap = e.R, e.D, e.cap
@@ -363,8 +367,8 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
     image = sc.image[: y1 - y0] if sc.image is not None else None
     eng = ShardedMergeEngine(H, W, R, D, C, xs.shape[0], dist, dev)
 
-    def step():
-        return eng.run(sc.labels, feats, cfg["tau"], image_tile=image, xs_local=xs, ys_local_rel=ys_rel)
+    def step(gather=False):
+        return eng.run(sc.labels, feats, cfg["tau"], image_tile=image, xs_local=xs, ys_local_rel=ys_rel, gather_outputs=gather)
 
     for _ in range(max(args.warmup, 3)):
         res = step()
@@ -380,10 +384,20 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
         torch.cuda.synchronize()
         dist.barrier()
     ms_local = ev0.elapsed_time(ev1) / args.steps
-    t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     launches = L.dm_launch_count() - launches0
+    # the same with the statistics all-reduced and the final edge list gathered on every rank
+    k_g = max(1, args.steps // 2)
+    step(True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(k_g):
+        step(True)
+    ev1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ms_local, ev0.elapsed_time(ev1) / k_g], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_gathered = float(t[0].item()), float(t[1].item())
 
     # end to end with HOST buffers on every rank (tile H2D, label-map tile D2H inside the timed region)
     host = {"labels": sc.labels.cpu().pin_memory(), "image": image.cpu().pin_memory(), "feats": feats.cpu().pin_memory(),
@@ -393,7 +407,8 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
 
     def e2e_step():
         d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        r = eng.run(d["labels"], d["feats"], cfg["tau"], image_tile=d["image"], xs_local=d["xs"], ys_local_rel=d["ys"])
+        r = eng.run(d["labels"], d["feats"], cfg["tau"], image_tile=d["image"], xs_local=d["xs"], ys_local_rel=d["ys"],
+                    gather_outputs=False)
         out_host.copy_(r.labels, non_blocking=True)
         torch.cuda.synchronize()
 
@@ -421,8 +436,12 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
                                     "NCCL edge-list all-gather + region-statistics all-reduce"),
                        "H": H, "W": W, "bands": C, "segments": R,
                        "points": int(sc.xs.shape[0]), "embed_dim": D, "tau": cfg["tau"], "parallelism": f"row-tiles x{world}",
+                       "result_form": "distributed (tile label maps, replicated root LUT, per-rank partial region statistics and "
+                                      "tile edge lists); ms_per_step_gathered = with the statistics all-reduced and the final "
+                                      "edge list gathered on every rank",
                        "l2_policy": "inputs larger than L2, no flush needed"},
             "merged_edges_per_s": res.merges / (ms * 1e-3), "segments_after": n_roots, "rounds": res.rounds,
+            "ms_per_step_gathered": ms_gathered,
             "e2e": {"value": H * W / float(tmax[0]) / 1e3, "unit": "Mpx/s", "ms_per_step": float(tmax[0]),
                     "h2d_bytes_per_step": int(t[1]), "d2h_bytes_per_step": int(t[2])},
             "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None, "clocks": clocks.summary(),

@@ -269,6 +269,10 @@ int dm_rows_pack(const uint8_t* flag, const float* rows, int64_t n_regions, int6
                  float* out_rows, int64_t capacity, int64_t* n_out_dev, dm_stream_t stream);
 int dm_rows_unpack(const int32_t* ids, const float* in_rows, const int64_t* n_dev, int64_t capacity,
                    int64_t n_regions, int64_t D, float* rows, int add, dm_stream_t stream);
+/* every slot of an all-gathered exchange buffer in one launch; slot = int64 count | pad to 16 B | int32 ids[cap] |
+ * float rows[cap][D]; zero != 0: the listed rows are cleared, else copied (ids distinct over all slots). */
+int dm_rows_unpack_slots(const void* slots, int64_t n_slots, int64_t slot_bytes, int64_t slot_capacity,
+                         int64_t n_regions, int64_t D, float* rows, int zero, dm_stream_t stream);
 
 /* ----------------------------------------------------------------------------------- *
  * R11 Contrastive pair loss forward + backward (Losses.py:34-38):
