@@ -82,3 +82,33 @@ def test_two_rank_gloo_exchange_reproduces_whole_scene(tmp_path, H, W, R):
     ps, pc, _ = o.pool_points_csr(off, ids, sc["feats"])
     assert np.array_equal(got["pcnt"], pc)
     np.testing.assert_allclose(got["psum"], ps, rtol=1e-5, atol=1e-5)       # fp32 sums: order differs across tiles
+
+
+def _slots_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from deepmerge_b200.sharded import all_gather_slots
+    # fixed-capacity slot = [count | payload]: what the sharded engine ships instead of variable-length lists
+    slot = torch.full((6,), -1, dtype=torch.int64)
+    n = 2 + rank
+    slot[0] = n
+    slot[1:1 + n] = torch.arange(n) + 100 * rank
+    g = all_gather_slots(slot, dist).view(world, 6)
+    parent = torch.tensor([0, 1, 2, 3, 4, 5], dtype=torch.int32)
+    if rank == 0:
+        parent[3] = 1                    # rank 0 learnt 3 ~ 1
+    else:
+        parent[3] = 2                    # rank 1 learnt 3 ~ 2: the min keeps 1, rank 1 re-unions 2 ~ 3 next iteration
+    dist.all_reduce(parent, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        np.savez(out, g=g.numpy(), parent=parent.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_slot_gather_and_parent_min(tmp_path):
+    out = str(tmp_path / "s.npz")
+    mp.spawn(_slots_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    assert got["g"][0].tolist() == [2, 0, 1, -1, -1, -1] and got["g"][1].tolist() == [3, 100, 101, 102, -1, -1]
+    assert got["parent"].tolist() == [0, 1, 2, 1, 4, 5]
