@@ -98,3 +98,36 @@ def test_sharded_equals_single_gpu_and_oracle(cuda, world, H, W, R, tau):
         assert np.array_equal(r[7], s)                                # band sums: integer all-reduce, exact
     single = merge_scene(T(sc["labels"]), T(sc["feats"]), tau, n_regions=n, image=T(sc["image"]), xs=T(sc["xs"]), ys=T(sc["ys"]))
     assert np.array_equal(single.labels.cpu().numpy(), full)
+
+
+def test_sharded_row_slot_overflow_is_reported(cuda):
+    """The sparse row exchange uses fixed-capacity slots; a slot that is too small must raise, never truncate."""
+    import torch
+    from deepmerge_b200.sharded import ShardedMergeEngine, points_in_tile, tile_bounds
+    H, W, R, world = 120, 256, 400, 2
+    sc = o.synth_scene(H, W, R, C=4)
+    n, D = sc["n_regions"], sc["feats"].shape[1]
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    fd = FakeDist(world)
+    errors = []
+
+    def rank_main(rank):
+        try:
+            fd.local.rank = rank
+            torch.cuda.set_device(cuda)
+            y0, y1 = tile_bounds(H, world, rank)
+            last = rank == world - 1
+            mine = points_in_tile(torch.from_numpy(sc["ys"]), y0, y1).numpy()
+            eng = ShardedMergeEngine(H, W, n, D, 4, len(mine), fd, cuda, row_capacity=2)
+            eng.run(T(sc["labels"][y0:y1 + (0 if last else 1)]), T(sc["feats"][mine]), 0.5, image_tile=T(sc["image"][y0:y1]),
+                    xs_local=T(sc["xs"][mine]), ys_local_rel=T(sc["ys"][mine] - y0))
+        except RuntimeError as e:
+            errors.append(str(e))
+        except Exception as e:
+            errors.append("unexpected: %r" % (e,))
+            fd.bar.abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert len(errors) == world and all("slot overflow" in e for e in errors), errors
