@@ -413,6 +413,10 @@ class MergeEngine:
                      L.dm_edges_rekey_workspace_bytes(cap)]
             self.ws_bytes = max(sizes)
             self.ws = e(self.ws_bytes, dt=_U8)
+            # pooling runs on its own stream beside the raster pass (independent until the merge loop): own workspace
+            self.ws_pool_bytes = L.dm_csr_workspace_bytes(N, R)
+            self.ws_pool = e(self.ws_pool_bytes, dt=_U8)
+            self.side = torch.cuda.Stream(dev)
             self.done = torch.cuda.Event()
 
     # ---- stages -------------------------------------------------------------------------
@@ -437,8 +441,8 @@ class MergeEngine:
             L.check(L.dm_points_region(_p(labels), labels.shape[0], self.W, labels.stride(0), _p(xs), _p(ys), N,
                                        _p(self.rop), s), "dm_points_region")
             region_of_point = self.rop
-        L.check(L.dm_csr_build(_p(region_of_point), N, self.R, _p(self.offsets), _p(self.pids), _p(self.ws),
-                               self.ws_bytes, s), "dm_csr_build")
+        L.check(L.dm_csr_build(_p(region_of_point), N, self.R, _p(self.offsets), _p(self.pids), _p(self.ws_pool),
+                               self.ws_pool_bytes, s), "dm_csr_build")
         L.check(L.dm_pool_points_csr(_p(self.offsets), _p(self.pids), _p(feats), feats.stride(0), self.R, self.D,
                                      _p(self.sum), _p(self.cnt), s), "dm_pool_points_csr")
 
@@ -480,8 +484,14 @@ class MergeEngine:
             raise ValueError("engine was sized for C=%d bands" % self.C)
         with torch.cuda.device(self.dev):
             while True:
+                # point pooling (membership, CSR, segment sums) only needs the labels: it runs on a side stream while
+                # the raster pass -- instruction-issue bound, light on memory -- and its edge sort occupy the main one
+                cur = torch.cuda.current_stream(self.dev)
+                self.side.wait_stream(cur)
+                with torch.cuda.stream(self.side):
+                    self._pool(labels, xs, ys, region_of_point, feats)
                 self._rag(labels, image, rows_own, top_border, bottom_border)
-                self._pool(labels, xs, ys, region_of_point, feats)
+                cur.wait_stream(self.side)
                 try:
                     rounds, merges = self._merge_loop(tau, max_rounds, mlp)
                     break

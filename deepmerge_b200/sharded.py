@@ -189,13 +189,18 @@ class ShardedMergeEngine:
             n_edges = e.counts[0:1]
             # (1) tile pass: fused RAG + band pooling; e.keys / e.blen = the tile's own edge list,
             #     e.perim = border + incident boundary lengths of THIS tile (a partial, like area and the band sums)
+            #     (the tile's point pooling only needs the labels: it runs beside the raster pass on the engine's side stream)
+            cur = torch.cuda.current_stream(e.dev)
+            e.side.wait_stream(cur)
+            with torch.cuda.stream(e.side):
+                e._pool(labels_tile, xs_local, ys_local_rel, None, feats_local)
             e._rag(labels_tile, image_tile, self.rows_own, self.rank == 0, self.rank == self.world - 1)
             # (2) which ranks see which region
             self.seen.copy_(e.area > 0)
             L.check(L.dm_mark_endpoints(_p(e.keys), _p(n_edges), cap, R, _p(self.seen), s), "dm_mark_endpoints")
             torch.mul(self.seen, 1 << self.rank, out=self.mask)
             # (3) pooled embeddings: per-tile partial sums; counts replicated, rows of regions seen by two ranks exchanged
-            e._pool(labels_tile, xs_local, ys_local_rel, None, feats_local)
+            cur.wait_stream(e.side)
             self.cnt_local.copy_(e.cnt)
             self.mask_cnt[R:].copy_(e.cnt)
             dist.all_reduce(self.mask_cnt, op=SUM, group=grp)       # masks: distinct bits, the sum is the OR
