@@ -416,6 +416,8 @@ class MergeEngine:
             # pooling runs on its own stream beside the raster pass (independent until the merge loop): own workspace
             self.ws_pool_bytes = L.dm_csr_workspace_bytes(N, R)
             self.ws_pool = e(self.ws_pool_bytes, dt=_U8)
+            self.ws_side_bytes = L.dm_merge_apply_workspace_bytes(R)
+            self.ws_side = e(self.ws_side_bytes, dt=_U8)
             self.side = torch.cuda.Stream(dev)
             self.done = torch.cuda.Event()
 
@@ -445,6 +447,12 @@ class MergeEngine:
                                self.ws_pool_bytes, s), "dm_csr_build")
         L.check(L.dm_pool_points_csr(_p(self.offsets), _p(self.pids), _p(feats), feats.stride(0), self.R, self.D,
                                      _p(self.sum), _p(self.cnt), s), "dm_pool_points_csr")
+
+    def _mean_all(self):
+        L = self.L
+        L.check(L.dm_region_mean(_p(self.sum), _p(self.cnt), self.R, self.D, _p(self.mean), _p(self.norm2), None, _stream()),
+                "dm_region_mean")
+        self._means_fresh = True
 
     def _read_counts(self):
         self.host_counts.copy_(self.counts, non_blocking=True)
@@ -490,6 +498,7 @@ class MergeEngine:
                 self.side.wait_stream(cur)
                 with torch.cuda.stream(self.side):
                     self._pool(labels, xs, ys, region_of_point, feats)
+                    self._mean_all()
                 self._rag(labels, image, rows_own, top_border, bottom_border)
                 cur.wait_stream(self.side)
                 try:
@@ -529,7 +538,9 @@ class MergeEngine:
         self.parent.copy_(self.iota)
         self.alive.fill_(1)
         self.counts[5:8].zero_()
-        L.check(L.dm_region_mean(_p(self.sum), _p(self.cnt), R, D, _p(self.mean), _p(self.norm2), None, s), "dm_region_mean")
+        if not getattr(self, "_means_fresh", False):      # run() computes them on the side stream right after the pooling
+            self._mean_all()
+        self._means_fresh = False
         self._score(mlp, None)
         rounds = merges = 0
         while True:
@@ -553,11 +564,17 @@ class MergeEngine:
             rounds += 1
             L.check(L.dm_uf_union(_p(self.parent), _p(self.keys), _p(self.selected), _p(n_edges), cap, s), "dm_uf_union")
             L.check(L.dm_uf_compress(_p(self.parent), R, s), "dm_uf_compress")
-            L.check(L.dm_merge_apply(_p(self.parent), _p(self.alive), _p(self.changed), _p(self.sum), _p(self.cnt),
-                                     _p(self.area), _p(self.perim), R, D, self.counts[5:6].data_ptr(), _p(self.ws),
-                                     self.ws_bytes, s), "dm_merge_apply")
+            # merged statistics (side stream) and edge re-keying (main stream) only share the parent array and integer
+            # atomics on the perimeter: two chains of small sort-dominated kernels that fill the GPU better together
+            cur = torch.cuda.current_stream(self.dev)
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                L.check(L.dm_merge_apply(_p(self.parent), _p(self.alive), _p(self.changed), _p(self.sum), _p(self.cnt),
+                                         _p(self.area), _p(self.perim), R, D, self.counts[5:6].data_ptr(), _p(self.ws_side),
+                                         self.ws_side_bytes, _stream()), "dm_merge_apply")
             L.check(L.dm_edges_rekey(_p(self.parent), _p(self.keys), _p(self.blen), _p(self.scores), _p(n_edges), cap, R,
                                      _p(self.perim), _p(self.ws), self.ws_bytes, s), "dm_edges_rekey")
+            cur.wait_stream(self.side)
             L.check(L.dm_region_mean(_p(self.sum), _p(self.cnt), R, D, _p(self.mean), _p(self.norm2), _p(self.changed), s),
                     "dm_region_mean")
             self._score(mlp, self.changed)

@@ -253,11 +253,14 @@ class ShardedMergeEngine:
                 L.check(L.dm_shard_plan(_p(e.parent), _p(e.alive), _p(self.mask_old), _p(self.mask), _p(self.grew), self.rank, R,
                                         _p(self.send), _p(self.seen_comp), s), "dm_shard_plan")
                 self._exchange_rows(self.send, add=False)
-                L.check(L.dm_merge_apply_masked(_p(e.parent), _p(e.alive), _p(e.changed), _p(e.sum), _p(e.cnt), _p(e.area),
-                                                _p(e.perim), R, D, e.counts[5:6].data_ptr(), _p(self.seen_comp), _p(e.ws),
-                                                e.ws_bytes, s), "dm_merge_apply_masked")
+                e.side.wait_stream(cur)                            # merged statistics beside the edge re-keying (as on one GPU)
+                with torch.cuda.stream(e.side):
+                    L.check(L.dm_merge_apply_masked(_p(e.parent), _p(e.alive), _p(e.changed), _p(e.sum), _p(e.cnt), _p(e.area),
+                                                    _p(e.perim), R, D, e.counts[5:6].data_ptr(), _p(self.seen_comp),
+                                                    _p(e.ws_side), e.ws_side_bytes, _stream()), "dm_merge_apply_masked")
                 L.check(L.dm_edges_rekey(_p(e.parent), _p(e.keys), _p(e.blen), _p(e.scores), _p(n_edges), cap, R, _p(e.perim),
                                          _p(e.ws), e.ws_bytes, s), "dm_edges_rekey")
+                cur.wait_stream(e.side)
                 L.check(L.dm_region_mean(_p(e.sum), _p(e.cnt), R, D, _p(e.mean), _p(e.norm2), _p(e.changed), s), "dm_region_mean")
                 L.check(L.dm_score_l2(_p(e.mean), _p(e.norm2), D, _p(e.keys), _p(n_edges), cap, _p(e.changed), _p(e.scores), s),
                         "dm_score_l2")
