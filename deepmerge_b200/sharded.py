@@ -431,8 +431,24 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    # the dominant kernel (fused raster pass over this rank's tile) alone, CUDA events
+    rows_t = y1 - y0
+    rk0 = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    rk1 = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    e = eng.eng
+    for i in range(5):
+        e.stats.zero_()
+        rk0[i].record()
+        L.check(L.dm_rag_scan(_p(sc.labels), rows_t, sc.labels.shape[0], W, W, _p(image), C, W * C, R, int(rank == 0),
+                              int(rank == world - 1), _p(e.area), _p(e.border), _p(e.bsum), _p(e.bsq), e.cap, _p(e.counts),
+                              _p(e.ws), e.ws_bytes, _stream()), "scan")
+        rk1[i].record()
+    torch.cuda.synchronize()
+    rag_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(rk0[1:], rk1[1:])]))
+    res = step()
     if rank == 0:
         peak, kind = measured_peaks()
+        alg = (4 + C) * rows_t * W + 12 * (3 * R // world) + 16 * (R // world) * C
         n_roots = int((res.root == torch.arange(R, device=dev, dtype=torch.int32)).sum())
         line = {
             "metric": "megapixels/sec end-to-end (RAG+pool+score+merge+relabel)", "value": H * W / ms / 1e3, "unit": "Mpx/s",
@@ -452,7 +468,11 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
             "ms_per_step_gathered": ms_gathered,
             "e2e": {"value": H * W / float(tmax[0]) / 1e3, "unit": "Mpx/s", "ms_per_step": float(tmax[0]),
                     "h2d_bytes_per_step": int(t[1]), "d2h_bytes_per_step": int(t[2])},
-            "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None, "clocks": clocks.summary(),
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "rag_pool_kernel (fused RAG + band pooling raster pass), rank 0's tile", "bound": "hbm",
+                         "achieved": alg / (rag_ms * 1e-3) / 1e9, "peak": peak, "peak_kind": kind, "unit": "GB/s",
+                         "frac": alg / (rag_ms * 1e-3) / 1e9 / peak, "ms": rag_ms, "algorithmic_bytes": alg, "traffic": None},
+            "cpu_baseline": None, "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
