@@ -97,18 +97,29 @@ __global__ void __launch_bounds__(256) region_mean_kernel(const float* __restric
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < R; r += nwarps) {
-        if (only && !only[r]) continue;
+    auto one = [&](int64_t r) {
         const float c = (float)max(cnt[r], 1);
         float n2 = 0.f;
         for (int d = lane; d < D; d += 32) {
-            const float m = __fdiv_rn(sum[r * D + d], c);
-            mean[r * D + d] = m;
-            n2 = __fmaf_rn(m, m, n2);
+            const float v = __fdiv_rn(sum[r * D + d], c);
+            mean[r * D + d] = v;
+            n2 = __fmaf_rn(v, v, n2);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
         if (lane == 0) norm2[r] = n2;
+    };
+    if (!only) {                                   // every region: one warp per region
+        for (int64_t r = warp0; r < R; r += nwarps) one(r);
+        return;
+    }
+    // sparse update: a warp takes 32 consecutive regions -- one coalesced look at the flags, then the flagged ones in turn
+    for (int64_t r0 = warp0 * 32; r0 < R; r0 += nwarps * 32) {
+        unsigned m = __ballot_sync(0xffffffffu, r0 + lane < R && only[r0 + lane]);
+        while (m) {
+            one(r0 + __ffs(m) - 1);
+            m &= m - 1;
+        }
     }
 }
 

@@ -93,7 +93,7 @@ class ShardedMergeEngine:
     flags of the tile pass are checked with that first read-back."""
 
     def __init__(self, H, W, n_regions, D, C, n_points_local, dist, device, group=None, slot_capacity=None,
-                 row_capacity=None):
+                 row_capacity=None, edge_capacity=None, replicated=False):
         from .raster import MergeEngine, default_edge_capacity
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
@@ -102,11 +102,15 @@ class ShardedMergeEngine:
         self.y0, self.y1 = tile_bounds(H, self.world, self.rank)
         self.rows_own = self.y1 - self.y0
         self.has_halo = self.rank < self.world - 1
-        # capacity: the global edge list (and the raw per-tile entries) must fit
-        cap = default_edge_capacity(n_regions, H, W)
-        self.slot_cap = int(slot_capacity) if slot_capacity else cap // self.world + 4 * W + 4096
-        self.eng = MergeEngine(self.rows_own, W, n_regions, D, C=C, n_points=n_points_local, edge_capacity=cap,
-                               device=device)
+        # capacity: the raw per-tile entries of THIS tile must fit (an even share of the regions plus 50 %; a scene
+        # whose regions crowd into one tile needs edge_capacity=...).  Kernel grids of the graph stages are sized by it.
+        from .raster import default_edge_capacity
+        glob_cap = default_edge_capacity(n_regions, H, W)
+        cap = int(edge_capacity) if edge_capacity else min(
+            glob_cap, default_edge_capacity(int(1.5 * n_regions / self.world) + 1024, self.rows_own + 1, W))
+        self.slot_cap = int(slot_capacity) if slot_capacity else glob_cap // self.world + 4 * W + 4096   # run_replicated only
+        self.eng = MergeEngine(self.rows_own, W, n_regions, D, C=C, n_points=n_points_local,
+                               edge_capacity=glob_cap if replicated else cap, device=device)   # run_replicated holds the global list
         dev = self.eng.dev
         self.tile_counts = torch.zeros(4, dtype=torch.int64, device=dev)
         self.cat_counts = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -133,10 +137,6 @@ class ShardedMergeEngine:
         self.slot_n = self.slot[:8].view(torch.int64)
         self.slot_ids = self.slot[16:16 + 4 * self.row_cap].view(torch.int32)
         self.slot_rows = self.slot[16 + 4 * self.row_cap:16 + 4 * self.row_cap * (D + 1)].view(torch.float32).view(self.row_cap, D)
-        # final edge-list gather: [count (16 B) | keys | lens]
-        self.eslot_bytes = 16 + 12 * self.slot_cap
-        self.eslot_bytes += (-self.eslot_bytes) % 16
-        self.eslot = z(self.eslot_bytes, dt=torch.uint8)
         self.flags = z(4, dt=torch.int64)                          # [0] selected (global), [1] parent changed, [2] slot overflow
         self.host_flags = torch.zeros(4, dtype=torch.int64).pin_memory()
 
@@ -271,26 +271,31 @@ class ShardedMergeEngine:
             if gather_outputs:
                 # per-tile partials -> global statistics; tile edge lists -> the global final edge list
                 allreduce_sum_(e.stats, dist, grp)                  # area | border | band sums | perimeter in one buffer
-                sc_ = self.slot_cap
-                self.eslot[:8].view(torch.int64).copy_(e.counts[0:1])
-                self.eslot[16:16 + 8 * sc_].view(torch.int64).copy_(e.keys[:sc_])
-                self.eslot[16 + 8 * sc_:16 + 12 * sc_].view(torch.int32).copy_(e.blen[:sc_])
-                ge = all_gather_slots(self.eslot, dist, grp).view(self.world, self.eslot_bytes)
-                gc = torch.stack([ge[r, :8].view(torch.int64)[0] for r in range(self.world)])
-                gk = torch.cat([ge[r, 16:16 + 8 * sc_].view(torch.int64) for r in range(self.world)])
-                gl = torch.cat([ge[r, 16 + 8 * sc_:16 + 12 * sc_].view(torch.int32) for r in range(self.world)])
-                L.check(L.dm_edges_concat(_p(gk), _p(gl), _p(gc), self.world, sc_, _p(e.keys), _p(e.blen), cap,
-                                          _p(self.cat_counts), s), "dm_edges_concat")
-                L.check(L.dm_edges_sort_unique(_p(e.keys), _p(e.blen), _p(self.cat_counts), cap, R, _p(e.counts), _p(e.ws),
-                                               e.ws_bytes, s), "dm_edges_sort_unique")
-                cc = torch.cat([e.counts[0:1], self.cat_counts[1:2]]).tolist()
-                if cc[1] != 0:
-                    raise RuntimeError("final edge list gather overflow (slot %d)" % self.slot_cap)
-                Ef = int(cc[0])
+                nmax = e.counts[0:1].clone()
+                dist.all_reduce(nmax, op=MAX, group=grp)
+                m = max(1, int(nmax.item()))                        # (the gathered form may afford this host round trip)
+                gk = all_gather_slots(e.keys[:m], dist, grp)
+                gl = all_gather_slots(e.blen[:m], dist, grp)
+                gc = all_gather_slots(e.counts[0:1], dist, grp)
+                tot = self.world * m
+                out_k = torch.empty(tot, dtype=torch.int64, device=e.dev)
+                out_l = torch.empty(tot, dtype=torch.int32, device=e.dev)
+                n_out = torch.zeros(2, dtype=torch.int64, device=e.dev)
+                L.check(L.dm_edges_concat(_p(gk), _p(gl), _p(gc), self.world, m, _p(out_k), _p(out_l), tot, _p(self.cat_counts), s),
+                        "dm_edges_concat")
+                wsb = L.dm_edges_unique_workspace_bytes(tot)
+                ws = torch.empty(wsb, dtype=torch.uint8, device=e.dev)
+                L.check(L.dm_edges_sort_unique(_p(out_k), _p(out_l), _p(self.cat_counts), tot, R, _p(n_out), _p(ws), wsb, s),
+                        "dm_edges_sort_unique")
+                Ef = int(n_out[0].item())
+                return MergeResult(e.out[: self.rows_own], e.parent, rounds, merges, out_k[:Ef], out_l[:Ef], None, e.area,
+                                   e.perim, e.sum, e.cnt)
         return MergeResult(e.out[: self.rows_own], e.parent, rounds, merges, e.keys[:Ef], e.blen[:Ef], None, e.area,
                            e.perim, e.sum, e.cnt)
 
     def run_replicated(self, labels_tile, feats_local, tau, *, image_tile=None, xs_local=None, ys_local_rel=None, max_rounds=64):
+        if self.eng.cap < self.slot_cap:
+            raise ValueError("run_replicated needs the engine built with replicated=True (global edge capacity)")
         """labels_tile: int32 [rows_own (+1 halo), W]; ys_local_rel are rows relative to the tile."""
         from .raster import MergeResult, _p, _stream
         e, L, dist = self.eng, self.eng.L, self.dist
