@@ -361,11 +361,70 @@ __global__ void __launch_bounds__(256) rows_unpack_slots_kernel(const unsigned c
     }
 }
 
+// fused R-sized glue of the distributed merge loop (one launch each instead of a string of elementwise kernels)
+__global__ void shard_seen_kernel(const int64_t* __restrict__ area, uint8_t* __restrict__ seen, const int32_t* __restrict__ cnt,
+                                  int my_bit, int64_t R, int32_t* __restrict__ mask_cnt, int32_t* __restrict__ cnt_local) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
+        const bool sees = seen[r] || area[r] > 0;            // an endpoint of a tile edge, or pixels in the tile
+        seen[r] = sees ? 1 : 0;
+        mask_cnt[r] = sees ? my_bit : 0;
+        const int c = cnt[r];
+        mask_cnt[R + r] = c;
+        cnt_local[r] = c;
+    }
+}
+__global__ void shard_frontier_kernel(const int32_t* __restrict__ mask_cnt, const int32_t* __restrict__ cnt_local, int64_t R,
+                                      int32_t* __restrict__ cnt, uint8_t* __restrict__ send) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
+        const int m = mask_cnt[r];
+        cnt[r] = mask_cnt[R + r];
+        send[r] = ((m & (m - 1)) != 0 && cnt_local[r] > 0) ? 1 : 0;   // seen by two ranks, and this one has points of it
+    }
+}
+__global__ void any_diff_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int64_t n,
+                                int64_t* __restrict__ flag) {
+    bool d = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        d |= a[i] != b[i];
+    if (__any_sync(0xffffffffu, d) && (threadIdx.x & 31) == 0) *flag = 1;
+}
+
 }  // namespace merge
 }  // namespace dm
 
 using namespace dm;
 using merge::grid_for;
+
+extern "C" int dm_shard_seen(const int64_t* area, uint8_t* seen, const int32_t* cnt, int rank, int64_t n_regions,
+                             int32_t* mask_cnt, int32_t* cnt_local, dm_stream_t stream) {
+    if (n_regions < 0 || rank < 0 || rank > 30) return DM_ERR_BAD_ARG;
+    if (n_regions == 0) return DM_OK;
+    if (!area || !seen || !cnt || !mask_cnt || !cnt_local) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::shard_seen_kernel<<<grid_for(n_regions), 256, 0, S(stream)>>>(area, seen, cnt, 1 << rank, n_regions, mask_cnt, cnt_local);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_shard_frontier(const int32_t* mask_cnt, const int32_t* cnt_local, int64_t n_regions, int32_t* cnt,
+                                 uint8_t* send, dm_stream_t stream) {
+    if (n_regions < 0) return DM_ERR_BAD_ARG;
+    if (n_regions == 0) return DM_OK;
+    if (!mask_cnt || !cnt_local || !cnt || !send) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::shard_frontier_kernel<<<grid_for(n_regions), 256, 0, S(stream)>>>(mask_cnt, cnt_local, n_regions, cnt, send);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_any_diff_i32(const int32_t* a, const int32_t* b, int64_t n, int64_t* flag_dev, dm_stream_t stream) {
+    if (n < 0 || !flag_dev) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    DM_CUDA(cudaMemsetAsync(flag_dev, 0, sizeof(int64_t), s));
+    if (n == 0) return DM_OK;
+    if (!a || !b) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::any_diff_kernel<<<grid_for(n), 256, 0, s>>>(a, b, n, flag_dev);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
 
 extern "C" int dm_rows_unpack_slots(const void* slots, int64_t n_slots, int64_t slot_bytes, int64_t slot_capacity,
                                     int64_t n_regions, int64_t D, float* rows, int zero, dm_stream_t stream) {

@@ -196,18 +196,15 @@ class ShardedMergeEngine:
                 e._pool(labels_tile, xs_local, ys_local_rel, None, feats_local)
             e._rag(labels_tile, image_tile, self.rows_own, self.rank == 0, self.rank == self.world - 1)
             # (2) which ranks see which region
-            self.seen.copy_(e.area > 0)
+            self.seen.zero_()
             L.check(L.dm_mark_endpoints(_p(e.keys), _p(n_edges), cap, R, _p(self.seen), s), "dm_mark_endpoints")
-            torch.mul(self.seen, 1 << self.rank, out=self.mask)
             # (3) pooled embeddings: per-tile partial sums; counts replicated, rows of regions seen by two ranks exchanged
             cur.wait_stream(e.side)
-            self.cnt_local.copy_(e.cnt)
-            self.mask_cnt[R:].copy_(e.cnt)
-            dist.all_reduce(self.mask_cnt, op=SUM, group=grp)       # masks: distinct bits, the sum is the OR
-            e.cnt.copy_(self.mask_cnt[R:])
+            L.check(L.dm_shard_seen(_p(e.area), _p(self.seen), _p(e.cnt), self.rank, R, _p(self.mask_cnt), _p(self.cnt_local), s),
+                    "dm_shard_seen")
+            dist.all_reduce(self.mask_cnt, op=SUM, group=grp)       # masks: distinct bits, the sum is the OR; counts add up
             self.flags.zero_()
-            frontier = (self.mask & (self.mask - 1)) != 0
-            self.send.copy_(frontier & (self.cnt_local > 0))
+            L.check(L.dm_shard_frontier(_p(self.mask_cnt), _p(self.cnt_local), R, _p(e.cnt), _p(self.send), s), "dm_shard_frontier")
             self._exchange_rows(self.send, add=True)
             # (4) merge loop on the tile's edges with the replicated parent array
             e.parent.copy_(e.iota)
@@ -243,7 +240,7 @@ class ShardedMergeEngine:
                         self.agreed.copy_(e.parent)
                         L.check(L.dm_uf_union(_p(e.parent), _p(e.keys), _p(e.selected), _p(n_edges), cap, s), "dm_uf_union")
                         L.check(L.dm_uf_compress(_p(e.parent), R, s), "dm_uf_compress")
-                    self.flags[1:2].copy_((e.parent != self.agreed).any().to(torch.int64))
+                    L.check(L.dm_any_diff_i32(_p(e.parent), _p(self.agreed), R, self.flags[1:2].data_ptr(), s), "dm_any_diff_i32")
                     dist.all_reduce(self.flags[1:2], op=MAX, group=grp)
                     if int(self.flags[1].item()) == 0:
                         break

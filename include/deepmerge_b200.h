@@ -263,6 +263,14 @@ int dm_shard_propagate(const int32_t* parent, const uint8_t* alive, int32_t* mas
 int dm_shard_plan(const int32_t* parent, const uint8_t* alive, const int32_t* mask_old, const int32_t* mask_new,
                   const uint8_t* grew, int rank, int64_t n_regions, uint8_t* send, uint8_t* seen_comp,
                   dm_stream_t stream);
+/* fused per-region glue: dm_shard_seen: seen[r] |= area[r] > 0; mask_cnt[r] = seen ? 1 << rank : 0; mask_cnt[R + r] =
+ * cnt_local[r] = cnt[r] (the buffer that is all-reduced).  dm_shard_frontier (after the all-reduce): cnt[r] = global count,
+ * send[r] = region seen by two ranks and this rank has points of it.  dm_any_diff_i32: flag_dev[0] = any(a != b). */
+int dm_shard_seen(const int64_t* area, uint8_t* seen, const int32_t* cnt, int rank, int64_t n_regions,
+                  int32_t* mask_cnt, int32_t* cnt_local, dm_stream_t stream);
+int dm_shard_frontier(const int32_t* mask_cnt, const int32_t* cnt_local, int64_t n_regions, int32_t* cnt, uint8_t* send,
+                      dm_stream_t stream);
+int dm_any_diff_i32(const int32_t* a, const int32_t* b, int64_t n, int64_t* flag_dev, dm_stream_t stream);
 int dm_mark_endpoints(const uint64_t* edge_keys, const int64_t* n_edges_dev, int64_t capacity, int64_t n_regions,
                       uint8_t* flags, dm_stream_t stream);
 int dm_rows_pack(const uint8_t* flag, const float* rows, int64_t n_regions, int64_t D, int32_t* out_ids,
