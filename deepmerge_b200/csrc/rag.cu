@@ -4,21 +4,30 @@
 // warp of a persistent grid (one 16-warp CTA per SM) owns a contiguous run of rows of one
 // strip and walks straight down it:
 //   * lane 0 of the warp feeds the warp's OWN ring of shared-memory stages with TMA
-//     (cp.async.bulk.tensor boxes of TH+1 label rows x 132 columns -- 1-row / 4-column halo
-//     -- and TH image rows), completion signalled on the warp's own mbarriers.  No producer
-//     warp, no block-level barrier anywhere after start-up: warps never wait for each other.
+//     (cp.async.bulk.tensor boxes of TH label rows x 132 columns -- a 4-column halo for the
+//     right neighbour -- and TH image rows), completion signalled on the warp's own
+//     mbarriers.  No producer warp, no block-level barrier anywhere after start-up: warps
+//     never wait for each other.  The row ABOVE a unit is carried in registers from the
+//     previous unit (read from global memory only at the start of a run / a strip).
 //   * every lane owns 4 consecutive pixels (one 128-bit LDS of labels, one of image bytes)
 //     and keeps a 2-entry register cache of per-label accumulators: area, border sides, C
 //     band sums and sums of squares, fed 4 pixels at a time with PRMT + DP4A on byte masks.
 //     Because the warp moves down contiguous rows, a cache entry lives for the whole height
-//     of a region.  Pixel pairs straddling the two cached labels are counted with the same
-//     byte masks (no per-pair work, no divergence); a third label nearby takes a slow path.
-//   * evictions go to the warp's private shared-memory hash tables (label -> accumulators,
-//     edge key -> pair count), which are drained to global memory with 64-bit atomics /
-//     appended (key,count) entries when half full.  The appended entries are then radix
-//     sorted and run-reduced (prims.cu) into the sorted unique edge list.
+//     of a region.  Vertical pairs are (row above, own row), so every label involved is
+//     already cached: two pixels of one entry are no pair, two pixels of different entries
+//     are a pair of the key (c0, c1), counted by popcount -- no label comparison, no
+//     divergence.  Junctions of three regions and nodata take a generic per-pair path.
+//   * evictions are pushed to a per-warp shared-memory queue, drained convergently into the
+//     warp's private hash tables (label -> accumulators, edge key -> pair count), which are
+//     drained to global memory with 64-bit atomics / appended (key,count) entries when half
+//     full.  The appended entries are then radix sorted and run-reduced (prims.cu) into the
+//     sorted unique edge list.
+// Things that matter for speed here (measured): shared-memory pointers must
+// keep their address space (no integer round trips: generic LD/ST/ATOM are far slower), runtime
+// picks must be selp chains (?: compiles to divergent branches), and every rare divergent block is
+// followed by __syncwarp() (otherwise the rest of the row runs once per divergent group).
 //
-// HBM traffic: labels 4 B/px + image C B/px read once (halo re-reads hit L2).
+// HBM traffic: labels 4 B/px + image C B/px read once.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -997,25 +1006,17 @@ static bool allow_tma_env() {
     return !(e && e[0] == '1');
 }
 
-// DM_RAG_CFG=n selects an alternative (rows per unit, stages, warps per CTA) shape for C = 4 (tuning knob).
+// Kernel shapes (rows per unit, pipeline stages, warps per CTA) per band count.  Measured alternatives for C = 4 on a
+// B200 (10k x 10k, ~1000-pixel regions): <4,4,2,16> 0.39 ms; <4,2,2,20> 0.42; <4,4,1,20> 0.38-0.43; <4,8,1,16> 0.38-0.45;
+// <4,2,3,16> 0.43; 24-28 warps spill (0.43-0.54 ms).  See DESIGN.md section 6.
 int run(const Params& P, int C, cudaStream_t s) {
     const bool tma = allow_tma_env();
-    const char* e = getenv("DM_RAG_CFG");
-    const int v = e ? atoi(e) : 0;
     switch (C) {
         case 0: return launch<Cfg<0, 8, 2, 16>>(P, tma, s);
         case 1: return launch<Cfg<1, 4, 3, 16>>(P, tma, s);
         case 2: return launch<Cfg<2, 4, 2, 16>>(P, tma, s);
         case 3: return launch<Cfg<3, 4, 2, 16>>(P, tma, s);
-        case 4:
-            switch (v) {
-                case 1: return launch<Cfg<4, 2, 2, 20>>(P, tma, s);
-                case 2: return launch<Cfg<4, 4, 1, 20>>(P, tma, s);
-                case 3: return launch<Cfg<4, 8, 1, 16>>(P, tma, s);
-                case 4: return launch<Cfg<4, 4, 2, 17>>(P, tma, s);
-                case 5: return launch<Cfg<4, 2, 3, 16>>(P, tma, s);
-                default: return launch<Cfg<4, 4, 2, 16>>(P, tma, s);
-            }
+        case 4: return launch<Cfg<4, 4, 2, 16>>(P, tma, s);
         default: return DM_ERR_BAD_ARG;
     }
 }
