@@ -440,3 +440,38 @@ def test_scene_pipeline_equals_single_calls(cuda):
     assert len(got) == 5
     for g, w in zip(got, want):
         assert np.array_equal(g, w)
+
+
+def test_rag_against_c_oracle_at_medium_size(cuda):
+    """3000 x 4096, 12k regions, 4 bands, nodata holes: bit-exact against the plain-C restatement (fast enough for this
+    size) and the whole merge against a recount of the merged map by the same C code."""
+    from deepmerge_b200 import build_rag, merge_scene
+    from oracle import build as oc
+    sc = o.synth_scene(3000, 4096, 12000, C=4)
+    L, R = sc["labels"].copy(), sc["n_regions"]
+    L[100:140, 900:1500] = -1
+    L[2990:, :17] = -1
+    rag = build_rag(T(L, cuda), R, T(sc["image"], cuda))
+    k, b, area, per = oc.build_rag(L, R)
+    assert np.array_equal(keys_np(rag.edge_keys), k) and np.array_equal(rag.boundary_len.cpu().numpy().view(np.uint32), b)
+    assert np.array_equal(rag.area.cpu().numpy(), area) and np.array_equal(rag.perimeter.cpu().numpy(), per)
+    s, q = oc.pool_bands(L, sc["image"], R)
+    assert np.array_equal(rag.band_sum.cpu().numpy().view(np.uint64), s)
+    assert np.array_equal(rag.band_sumsq.cpu().numpy().view(np.uint64), q)
+    res = merge_scene(T(sc["labels"], cuda), T(sc["feats"], cuda), 0.5, n_regions=R, image=T(sc["image"], cuda),
+                      xs=T(sc["xs"], cuda), ys=T(sc["ys"], cuda))
+    root = res.root.cpu().numpy()
+    assert np.array_equal(res.labels.cpu().numpy(), oc.relabel(sc["labels"], root))
+    k2, b2, area2, per2 = oc.build_rag(res.labels.cpu().numpy(), R)
+    roots = np.unique(root)
+    assert np.array_equal(keys_np(res.edge_keys), k2) and np.array_equal(res.boundary_len.cpu().numpy().view(np.uint32), b2)
+    assert np.array_equal(res.area.cpu().numpy()[roots], area2[roots])
+    assert np.array_equal(res.perimeter.cpu().numpy()[roots], per2[roots])
+    # the selected edges of the first round, recomputed on the CPU from the GPU's own scores, give the same roots
+    g0 = merge_scene(T(sc["labels"], cuda), T(sc["feats"], cuda), 0.5, n_regions=R, xs=T(sc["xs"], cuda), ys=T(sc["ys"], cuda),
+                     max_rounds=0)
+    sel = g0.scores.cpu().numpy() < 0.5
+    kk = keys_np(g0.edge_keys)[sel]
+    r1 = oc.min_roots(R, (kk >> np.uint64(32)).astype(np.int32), (kk & np.uint64(0xFFFFFFFF)).astype(np.int32))
+    if res.rounds == 1:
+        assert np.array_equal(r1, root)
