@@ -633,7 +633,7 @@ __device__ __forceinline__ void process_row(Thread<C>& th, const int4 a, const i
             }
         }
     }
-    __syncwarp();
+    // (no __syncwarp here: only register moves follow, and the next row's full-mask shuffle reconverges the warp)
     th.up = a;
     th.u0 = m0;
     th.u1 = m1;
@@ -815,19 +815,22 @@ rag_pool_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant_
         // a unit is "special" when it touches an image border: only those pay for border logic
         const bool special = (sx == 0) || (sx == P.tiles_x - 1) || (unit_y0 == 0) || (unit_y0 + TH >= P.rows_own);
         if (!special) {
+            const int* Lp = L + 4 * lane;                       // running row pointers: no per-row index arithmetic
+            const unsigned* Ip = I + CF::CW * lane;
+            const int* Lend = Lp + TH * LAB_PITCH;
 #pragma unroll 1
-            for (int r = 0; r < TH; ++r) {
-                const int4 a = *(const int4*)(L + r * LAB_PITCH + 4 * lane);
+            for (; Lp != Lend; Lp += LAB_PITCH, Ip += CF::IMG_ROW_WORDS) {
+                const int4 a = *(const int4*)Lp;
                 int right = __shfl_down_sync(0xffffffffu, a.x, 1);
-                if (lane == 31) right = L[r * LAB_PITCH + STRIP_W];
+                if (lane == 31) right = Lp[4];                  // the strip's 4-column halo starts right after lane 31's pixels
                 unsigned W[CF::CW], TB[CF::CW];
                 if (C > 0) {
                     if (C == 4) {
-                        const uint4 v = *(const uint4*)(I + r * CF::IMG_ROW_WORDS + 4 * lane);
+                        const uint4 v = *(const uint4*)Ip;
                         W[0] = v.x; W[1 % CF::CW] = v.y; W[2 % CF::CW] = v.z; W[3 % CF::CW] = v.w;
                     } else {
 #pragma unroll
-                        for (int c = 0; c < C; ++c) W[c] = I[r * CF::IMG_ROW_WORDS + C * lane + c];
+                        for (int c = 0; c < C; ++c) W[c] = Ip[c];
                     }
                     band_transpose<C>(W, TB);
                 }
