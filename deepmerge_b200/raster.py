@@ -596,8 +596,12 @@ class ScenePipeline:
 
     KEYS = ("labels", "image", "feats", "xs", "ys")
 
-    def __init__(self, engine: "MergeEngine"):
+    def __init__(self, engine: "MergeEngine", run_fn=None):
+        """run_fn(device_inputs: dict, tau, **kw) -> result with .labels living in engine.out; default: engine.run.
+        A ShardedMergeEngine passes its own run (engine = its tile engine): every rank then pipelines its tile."""
         self.eng = engine
+        self.run_fn = run_fn or (lambda d, tau, **kw: engine.run(d["labels"], d["feats"], tau, image=d.get("image"),
+                                                                  xs=d.get("xs"), ys=d.get("ys"), **kw))
         dev = engine.dev
         with torch.cuda.device(dev):
             self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -643,7 +647,7 @@ class ScenePipeline:
                 cur.wait_event(self.out_done[i])             # label map k-2 has left dev_out[i]
             d = self.dev_in[i]
             eng.out = self.dev_out[i]
-            res = eng.run(d["labels"], d["feats"], tau, image=d.get("image"), xs=d.get("xs"), ys=d.get("ys"), **kw)
+            res = self.run_fn(d, tau, **kw)
             done = torch.cuda.Event()
             done.record(cur)
             self.in_free[i] = done
