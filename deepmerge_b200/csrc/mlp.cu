@@ -2,7 +2,7 @@
 // 5th-generation tensor cores: three Linear + leaky_relu(0.01), bf16 operands, fp32 accumulation
 // in TMEM.
 //
-// One persistent CTA per SM walks over tiles of 128 rows (edges).  Fourteen warps, four roles:
+// One persistent CTA per SM walks over tiles of 128 rows (edges).  Eighteen warps, four roles:
 //   warp 0      weight loader: streams the pre-packed bf16 weight chunks (K = 64 columns of all
 //               256 output features, 32 KB, already in the UMMA SWIZZLE_128B K-major image) from
 //               global memory into a 3-stage shared-memory ring with 1-D TMA bulk copies
@@ -15,7 +15,7 @@
 //   warps 2-9   epilogue: tcgen05.ld the accumulator (each warp its TMEM lane quadrant), add the bias,
 //               apply the leaky ReLU, and either re-pack the activations as the next layer's bf16 A
 //               operand in shared memory or store the fp32 result;
-//   warps 10-13 producers (layer 1): gather the tile's rows -- x_e = concat(mean[lo], mean[hi]) --
+//   warps 10-17 producers (layer 1): gather the tile's rows -- x_e = concat(mean[lo], mean[hi]) --
 //               convert to bf16 and write them as swizzled A chunks into the ring, running ahead of
 //               the tile in flight as far as the ring allows.
 // Layers 2 and 3 never leave the SM: h1 and h2 go TMEM -> registers -> shared memory -> tensor core.
@@ -43,11 +43,12 @@ constexpr int OFF_A2 = OFF_RING + STAGES * STAGE_BYTES;
 constexpr int OFF_W3 = OFF_A2 + A2_BYTES;
 constexpr int OFF_BIAS = OFF_W3 + W3_BYTES;
 constexpr int OFF_BARS = OFF_BIAS + BIAS_FLOATS * 4;
-constexpr int N_BARS = 3 * STAGES + 5;                       // full_b, full_a, empty per stage; d1/d2/d3_full; a1/a2_ready
+constexpr int N_BARS = 3 * STAGES + 3 + 8;                   // full_b, full_a, empty per stage; d1/d2/d3_full; a1/a2_ready per K chunk
 constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
 constexpr int SMEM_BYTES = 1024 + OFF_TMEM + 16;
 constexpr int EPI_WARPS = 8;                 // two per TMEM lane quadrant, each half of the columns
-constexpr int THREADS = (2 + EPI_WARPS + 4) * 32;   // loader, MMA issuer, epilogue warps, 4 producer warps
+constexpr int PROD_WARPS = 8;                // each gathers 128 / PROD_WARPS rows of a chunk
+constexpr int THREADS = (2 + EPI_WARPS + PROD_WARPS) * 32;   // loader, MMA issuer, epilogue warps, producer warps
 constexpr int TMEM_COLS = 512;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_A2 % 1024 == 0 && OFF_W3 % 1024 == 0 && STAGE_BYTES % 1024 == 0 && A_CHUNK_BYTES % 1024 == 0, "swizzle atoms");
@@ -165,6 +166,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // byte offset of the 16-byte piece p (8 bf16) of row r inside a [rows x 64] swizzled chunk
 __device__ __forceinline__ uint32_t swz(int r, int p) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((p ^ (r & 7)) << 4)); }
 
+// epilogue half 0 writes chunks 0, 1 while half 1 writes 2, 3: the i-th chunk to be complete is kc_order(i)
+__host__ __device__ constexpr int kc_order(int i) { return ((i & 1) << 1) | (i >> 1); }
+
 struct Ring {            // every role walks the same sequence of ring uses
     int stage = 0;
     unsigned phase = 0;
@@ -190,7 +194,9 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
     auto empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
     // accumulator / activation hand-offs, each completing once per tile (parity = tile iteration & 1)
     const uint32_t d1_full = bar0 + 8u * (3 * STAGES), d2_full = d1_full + 8u, d3_full = d1_full + 16u;
-    const uint32_t a1_ready = d1_full + 24u, a2_ready = d1_full + 32u;
+    // activations are handed over per 64-column chunk (= one K chunk of the next layer): a1_ready(kc), a2_ready(kc)
+    auto a1_ready = [&](int kc) { return d1_full + 24u + 8u * kc; };
+    auto a2_ready = [&](int kc) { return d1_full + 24u + 32u + 8u * kc; };
 
     const int64_t n_rows = P.n_dev ? *P.n_dev : P.n_host;
     const int64_t tiles = (n_rows + M_TILE - 1) / M_TILE;
@@ -205,14 +211,16 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_b(s), 1);
-            mbar_init(full_a(s), 4);
+            mbar_init(full_a(s), PROD_WARPS);
             mbar_init(empty(s), 1);
         }
         mbar_init(d1_full, 1);
         mbar_init(d2_full, 1);
         mbar_init(d3_full, 1);
-        mbar_init(a1_ready, EPI_WARPS);
-        mbar_init(a2_ready, EPI_WARPS);
+        for (int kc = 0; kc < N_HID / KC; ++kc) {
+            mbar_init(a1_ready(kc), 4);       // the four warps (TMEM lane quadrants) that write that 64-column chunk
+            mbar_init(a2_ready(kc), 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -234,7 +242,9 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
             for (int kc = 0; kc < nk1 + nk2; ++kc) {
                 mbar_wait(empty(ring.stage), ring.phase ^ 1u, P.status);
                 if (lane == 0) {
-                    const unsigned char* src = P.packed + (size_t)kc * B_CHUNK_BYTES;    // W1 chunks, then W2 chunks
+                    // W1 chunks in order, then W2 chunks in the order the epilogue halves finish them: 0, 2, 1, 3
+                    const int ck = kc < nk1 ? kc : nk1 + kc_order(kc - nk1);
+                    const unsigned char* src = P.packed + (size_t)ck * B_CHUNK_BYTES;
                     mbar_expect_tx(full_b(ring.stage), B_CHUNK_BYTES);
                     bulk_g2s(sbase + OFF_RING + ring.stage * STAGE_BYTES + A_CHUNK_BYTES, src, B_CHUNK_BYTES,
                              full_b(ring.stage));
@@ -272,9 +282,9 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
         unsigned it = 0;
         for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
             // layer 2: D2 = h1 W2^T, A from the resident activation buffer, B from the ring
-            mbar_wait(a1_ready, it & 1u, P.status);
-            tc_fence_after();
-            for (int kc = 0; kc < nk2; ++kc) {
+            for (int i = 0; i < nk2; ++i) {
+                const int kc = kc_order(i);                               // h1 chunk kc is ready as soon as its half wrote it
+                mbar_wait(a1_ready(kc), it & 1u, P.status);
                 mbar_wait(full_b(ring.stage), ring.phase, P.status);
                 tc_fence_after();
                 if (lane == 0) {
@@ -282,16 +292,17 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
                     const uint32_t b0 = sbase + OFF_RING + ring.stage * STAGE_BYTES + A_CHUNK_BYTES;
 #pragma unroll
                     for (int k = 0; k < KC / UMMA_K; ++k)
-                        tc_mma(tmem + N_HID, umma_desc(a0 + k * 32), umma_desc(b0 + k * 32), idesc_hid, (kc | k) ? 1u : 0u);
+                        tc_mma(tmem + N_HID, umma_desc(a0 + k * 32), umma_desc(b0 + k * 32), idesc_hid, (i | k) ? 1u : 0u);
                     tc_commit(empty(ring.stage));
-                    if (kc == nk2 - 1) tc_commit(d2_full);
+                    if (i == nk2 - 1) tc_commit(d2_full);
                 }
                 __syncwarp();
                 ring.advance();
             }
             if (tile + gridDim.x < tiles) issue_l1();          // next tile's layer 1 overlaps this tile's epilogue 2
             // layer 3: D3 = h2 W3^T, both operands resident; D3 takes over D2's columns (E2 has read them)
-            mbar_wait(a2_ready, it & 1u, P.status);
+            // (D3 overwrites D2's first 16 columns: wait for ALL of epilogue 2 before the first layer-3 MMA)
+            for (int i = 0; i < nk2; ++i) mbar_wait(a2_ready(i), it & 1u, P.status);
             tc_fence_after();
             if (lane == 0) {
                 for (int kc = 0; kc < nk2; ++kc) {
@@ -307,16 +318,18 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
     } else if (warp >= 2 + EPI_WARPS) {
         // ===== producers: gather the tile's rows, convert to bf16, write swizzled A chunks (layer 1) ========
         Ring ring;
-        const int w = warp - (2 + EPI_WARPS);         // 0..3
+        const int w = warp - (2 + EPI_WARPS);         // 0 .. PROD_WARPS-1
+        constexpr int RPW = M_TILE / PROD_WARPS;      // rows per producer warp
+        constexpr int ITS = RPW / 4;                  // 4 rows per warp instruction (8 lanes x 16 bytes per row chunk)
         const int piece = lane & 7, rsub = lane >> 3; // 16-byte piece / row within a 4-row group
         for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             const int64_t row0 = tile * M_TILE;
-            // rows this thread gathers: w*32 + it*4 + rsub, it = 0..7
-            const float* base_lo[8];
-            const float* base_hi[8];
+            // rows this thread gathers: w*RPW + it*4 + rsub
+            const float* base_lo[ITS];
+            const float* base_hi[ITS];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int64_t e = row0 + w * 32 + it * 4 + rsub;
+            for (int it = 0; it < ITS; ++it) {
+                const int64_t e = row0 + w * RPW + it * 4 + rsub;
                 base_lo[it] = base_hi[it] = nullptr;
                 if (e < n_rows) {
                     if (P.keys) {
@@ -335,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
                 unsigned char* a_st = smem + OFF_RING + ring.stage * STAGE_BYTES;
                 const int k0 = kc * KC + piece * 8;
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
+                for (int it = 0; it < ITS; ++it) {
                     float v[8];
                     if (vec4) {                       // D, ld multiples of 4 and a 16-byte aligned base: 128-bit gathers
 #pragma unroll
@@ -355,7 +368,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
                             v[j] = x;
                         }
                     }
-                    const int r = w * 32 + it * 4 + rsub;
+                    const int r = w * RPW + it * 4 + rsub;
                     *(uint4*)(a_st + swz(r, piece)) =
                         make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                 }
@@ -407,11 +420,13 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
                         *(uint4*)(a2 + swz(r, (c0 % KC) / 8 + i)) =
                             make_uint4(pack_bf16(h[8 * i], h[8 * i + 1]), pack_bf16(h[8 * i + 2], h[8 * i + 3]),
                                        pack_bf16(h[8 * i + 4], h[8 * i + 5]), pack_bf16(h[8 * i + 6], h[8 * i + 7]));
+                    if ((c0 & (KC - 1)) == KC - 32) {                     // a 64-column chunk is complete: hand it over
+                        tc_fence_before();
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(layer == 0 ? a1_ready(c0 / KC) : a2_ready(c0 / KC));
+                    }
                 }
-                tc_fence_before();
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(layer == 0 ? a1_ready : a2_ready);
             }
             // ---- epilogue 3: o = lrelu(D3 + b3) ------------------------------------------------------
             // every epilogue warp waits (the next tile's h1 must not overwrite h2 before layer 3 has read it)
