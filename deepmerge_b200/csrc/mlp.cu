@@ -2,7 +2,7 @@
 // 5th-generation tensor cores: three Linear + leaky_relu(0.01), bf16 operands, fp32 accumulation
 // in TMEM.
 //
-// One persistent CTA per SM walks over tiles of 128 rows (edges).  Eighteen warps, four roles:
+// One persistent CTA per SM walks over tiles of 128 rows (edges).  Twenty-six warps, four roles:
 //   warp 0      weight loader: streams the pre-packed bf16 weight chunks (K = 64 columns of all
 //               256 output features, 32 KB, already in the UMMA SWIZZLE_128B K-major image) from
 //               global memory into a 3-stage shared-memory ring with 1-D TMA bulk copies
@@ -15,7 +15,7 @@
 //   warps 2-9   epilogue: tcgen05.ld the accumulator (each warp its TMEM lane quadrant), add the bias,
 //               apply the leaky ReLU, and either re-pack the activations as the next layer's bf16 A
 //               operand in shared memory or store the fp32 result;
-//   warps 10-17 producers (layer 1): gather the tile's rows -- x_e = concat(mean[lo], mean[hi]) --
+//   warps 10-25 producers (layer 1): gather the tile's rows -- x_e = concat(mean[lo], mean[hi]) --
 //               convert to bf16 and write them as swizzled A chunks into the ring, running ahead of
 //               the tile in flight as far as the ring allows.
 // Layers 2 and 3 never leave the SM: h1 and h2 go TMEM -> registers -> shared memory -> tensor core.
@@ -47,7 +47,7 @@ constexpr int N_BARS = 3 * STAGES + 3 + 8;                   // full_b, full_a, 
 constexpr int OFF_TMEM = OFF_BARS + N_BARS * 8;
 constexpr int SMEM_BYTES = 1024 + OFF_TMEM + 16;
 constexpr int EPI_WARPS = 8;                 // two per TMEM lane quadrant, each half of the columns
-constexpr int PROD_WARPS = 8;                // each gathers 128 / PROD_WARPS rows of a chunk
+constexpr int PROD_WARPS = 16;               // each gathers 128 / PROD_WARPS rows of a chunk
 constexpr int THREADS = (2 + EPI_WARPS + PROD_WARPS) * 32;   // loader, MMA issuer, epilogue warps, producer warps
 constexpr int TMEM_COLS = 512;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
