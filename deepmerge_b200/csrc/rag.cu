@@ -46,7 +46,7 @@ constexpr int EQ = 64;                  // edge eviction queue entries per warp
 constexpr int FLUSH_ROWS = 256;         // forced drain period: 128 px * 256 rows * 255^2 < 2^32
 constexpr int EMPTY_LABEL = -1;
 constexpr unsigned long long EMPTY_KEY = ~0ull;
-constexpr int SLOT_UNKNOWN = -2, SLOT_NONE = -1;
+constexpr int SLOT_NONE = -1;
 
 constexpr int align128(int x) { return (x + 127) / 128 * 128; }
 
