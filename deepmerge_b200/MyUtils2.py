@@ -131,3 +131,24 @@ def cut_image(image, window):
     if dw > 0 and dh > 0:
         out[:, oy:oy + dh, ox:ox + dw] = image[:, y0:y0 + dh, x0:x0 + dw]
     return out
+
+
+def cut_windows(image, xpix, ylin, size):
+    """Batched cut_image on the GPU (dm_cut_windows): image uint8 CUDA tensor [C, H, W] (band-major, as GDAL reads
+    it), pixel centres (xpix, ylin) -> uint8 [n, C, size, size] windows whose top-left corners follow
+    calculate_left_top_point_and_size, zero-padded outside the raster (MyUtils2.py:330-383)."""
+    import torch
+    from ._lib import lib
+    from .raster import _p, _stream
+    if not image.is_cuda or image.dtype != torch.uint8 or image.dim() != 3:
+        raise ValueError("image must be a uint8 CUDA tensor [C, H, W]")
+    image = image.contiguous()
+    C, H, W = image.shape
+    left, top, _, _ = calculate_left_top_point_and_size(np.asarray(xpix), np.asarray(ylin), np.full(len(xpix), size))
+    x0 = torch.as_tensor(left, dtype=torch.int32, device=image.device)
+    y0 = torch.as_tensor(top, dtype=torch.int32, device=image.device)
+    out = torch.empty((len(xpix), C, size, size), dtype=torch.uint8, device=image.device)
+    L = lib()
+    with torch.cuda.device(image.device):
+        L.check(L.dm_cut_windows(_p(image), C, H, W, _p(x0), _p(y0), len(xpix), size, _p(out), _stream()), "dm_cut_windows")
+    return out

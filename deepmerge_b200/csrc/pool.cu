@@ -230,6 +230,30 @@ __global__ void __launch_bounds__(256) pool_boundary_kernel(const int32_t* __res
     }
 }
 
+// N1 (first piece): batched zero-padded window cut around sample points, the semantics of
+// ExtractFeatureDataset.cut_image (MyUtils2.py:330-360) on a band-major uint8 raster [C, H, W]:
+// out[i, c, v, u] = image[c, y0_i + v, x0_i + u] inside the raster, 0 outside.  One warp per output row.
+__global__ void __launch_bounds__(256) cut_windows_kernel(const uint8_t* __restrict__ image, int C, int64_t H, int64_t W,
+                                                          const int32_t* __restrict__ x0s, const int32_t* __restrict__ y0s,
+                                                          int64_t n, int size, uint8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t rows = n * C * size;
+    for (int64_t w = warp0; w < rows; w += nwarps) {
+        const int64_t i = w / ((int64_t)C * size);
+        const int c = (int)((w / size) % C), v = (int)(w % size);
+        const int64_t y = (int64_t)y0s[i] + v, x0 = x0s[i];
+        uint8_t* dst = out + w * size;
+        const bool row_in = y >= 0 && y < H;
+        const uint8_t* src = image + ((int64_t)c * H + (row_in ? y : 0)) * W;
+        for (int u = lane; u < size; u += 32) {
+            const int64_t x = x0 + u;
+            dst[u] = (row_in && x >= 0 && x < W) ? src[x] : (uint8_t)0;
+        }
+    }
+}
+
 static unsigned grid_for(int64_t work_items, int threads, int per_sm) {
     int64_t g = ceil_div(work_items, threads);
     int64_t cap = (int64_t)num_sms() * per_sm;
@@ -363,6 +387,17 @@ extern "C" int dm_pool_boundary(const int32_t* labels, int64_t rows_own, int64_t
         DM_COUNT_LAUNCH(); pool::pool_boundary_kernel<float><<<g, 256, 0, s>>>(labels, rows_own, W, ld, rows_avail, (const float*)emb, (int)D,
                                                                 edge_keys, n_edges_dev, bsum, bcnt);
     }
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_cut_windows(const uint8_t* image, int64_t C, int64_t H, int64_t W, const int32_t* x0, const int32_t* y0,
+                              int64_t n, int64_t size, uint8_t* out, dm_stream_t stream) {
+    if (C < 1 || H < 0 || W < 0 || n < 0 || size < 1 || size > (1 << 14)) return DM_ERR_BAD_ARG;
+    if (n == 0) return DM_OK;
+    if (!image || !x0 || !y0 || !out) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); pool::cut_windows_kernel<<<pool::grid_for(n * C * size * 32, 256, 8), 256, 0, S(stream)>>>(image, (int)C, H, W, x0, y0, n,
+                                                                                           (int)size, out);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

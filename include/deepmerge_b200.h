@@ -169,6 +169,13 @@ int dm_pool_boundary(const int32_t* labels, int64_t rows_own, int64_t rows_avail
                      const void* emb, int dtype_bf16, int64_t D, const uint64_t* edge_keys,
                      const int64_t* n_edges_dev, int64_t capacity, float* bsum, int32_t* bcnt, dm_stream_t stream);
 
+/* "Next" row N1, first piece: batched zero-padded window cut around sample points with the semantics of
+ * ExtractFeatureDataset.cut_image (MyUtils2.py:330-360) on a band-major uint8 raster [C, H, W] (what GDAL
+ * ReadAsArray returns): out uint8 [n, C, size, size], out[i,c,v,u] = image[c, y0[i]+v, x0[i]+u] or 0 outside.
+ * (x0, y0) = calculate_left_top_point_and_size(XPixel, YLine, size), MyUtils2.py:379-383. */
+int dm_cut_windows(const uint8_t* image, int64_t C, int64_t H, int64_t W, const int32_t* x0, const int32_t* y0,
+                   int64_t n, int64_t size, uint8_t* out, dm_stream_t stream);
+
 /* ----------------------------------------------------------------------------------- *
  * R6  Edge score = Euclidean distance between pooled means, the reference's expanded
  *     formula sqrt(max(0,|x|^2+|y|^2-2x.y)) in fp32 (ExtractFeatures.py:119-147, called

@@ -72,3 +72,22 @@ def test_pair_training_step_gather_plus_loss(cuda):
     np.testing.assert_allclose(loss.item(), want, rtol=1e-5)
     loss.backward()
     np.testing.assert_allclose(ga.grad.cpu().numpy(), wga, rtol=1e-4, atol=1e-8)
+
+
+def test_cut_windows_matches_reference_cutter(cuda, golden_dir):
+    """N1 first piece: the batched GPU window cut reproduces ExtractFeatureDataset.cut_image (executed reference,
+    golden geometry.npz) bit for bit, including windows that hang over every border and a 1 x 1 window."""
+    import torch
+    from deepmerge_b200 import MyUtils2 as m
+    g = np.load(os.path.join(golden_dir, "geometry.npz"))
+    img = torch.from_numpy(g["arr"]).to(cuda)
+    for i, (x, y, w) in enumerate(g["mids"]):
+        got = m.cut_windows(img, [int(x)], [int(y)], int(w))[0].cpu().numpy()
+        assert np.array_equal(got, g[f"cut{i}"]), i
+    # a batch of same-sized windows against the host mirror of the cutter
+    rng = np.random.default_rng(0)
+    xs, ys = rng.integers(-5, 56, size=64), rng.integers(-5, 46, size=64)
+    got = m.cut_windows(img, xs, ys, 9).cpu().numpy()
+    for k in range(64):
+        win = m.calculate_left_top_point_and_size(int(xs[k]), int(ys[k]), 9)
+        assert np.array_equal(got[k], m.cut_image(g["arr"], win))
