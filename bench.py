@@ -368,7 +368,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--side", type=int, default=0, help="debug: run a reduced side x side scene instead of configs[1]")
-    ap.add_argument("--cpu-side", type=int, default=2000, help="side of the bounded CPU sample")
+    ap.add_argument("--cpu-side", type=int, default=3000,
+                    help="side of the bounded CPU sample scenes (one per host core; ~1.4 s of numpy work each per step)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--config2", action="store_true",
                     help="N > 1 only: run BASELINE.json configs[2] (ONE 40k x 40k scene, ~1M segments, split over the ranks) "
