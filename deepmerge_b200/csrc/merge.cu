@@ -174,16 +174,6 @@ __global__ void rekey_kernel(const int32_t* __restrict__ parent, const uint64_t*
     }
 }
 
-__global__ void copy_edges_kernel(const uint64_t* __restrict__ k, const uint32_t* __restrict__ l, const float* __restrict__ s,
-                                  const int64_t* __restrict__ n_dev, uint64_t* __restrict__ ko, uint32_t* __restrict__ lo,
-                                  float* __restrict__ so) {
-    const int64_t n = *n_dev;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        ko[e] = k[e];
-        lo[e] = l[e];
-        if (s) so[e] = s[e];
-    }
-}
 
 // ---- relabel ------------------------------------------------------------------------------------
 __device__ __forceinline__ int lut(const int32_t* __restrict__ root, int l, int R) {
@@ -567,7 +557,7 @@ extern "C" int dm_merge_apply_masked(const int32_t* parent, uint8_t* alive, uint
                                                               (unsigned long long*)n_list, (unsigned long long*)n_merged,
                                                               root_mask);
     const int b = bits_for(R);
-    DM_TRY(prims::sort_pairs(list, nullptr, n_list, R, b, 2 * b, sws, s));
+    DM_TRY(prims::sort_pairs(list, nullptr, n_list, R, b, 2 * b, sws, s, prims::sort_fused_mode() >= 2));
     DM_COUNT_LAUNCH(); merge::merge_sums_kernel<<<grid_for(R * 32), 256, 0, s>>>(list, n_list, sum, (int)D);
     DM_LAUNCH_CHECK();
     return DM_OK;
@@ -606,12 +596,9 @@ extern "C" int dm_edges_rekey(const int32_t* parent, uint64_t* keys, uint32_t* l
     DM_COUNT_LAUNCH(); merge::rekey_kernel<<<grid_for(capacity), 256, 0, s>>>(parent, keys, lens, n_dev, sentinel,
                                                            (unsigned long long*)perimeter, nk, perm);
     const int b = bits_for(R + 1);
-    DM_TRY(prims::sort_pairs(nk, perm, n_dev, capacity, b, 2 * b, sws, s));
     int64_t* n_new = c.take<int64_t>(1);
-    DM_TRY(prims::unique_reduce(nk, perm, lens, scores, n_dev, capacity, sentinel, ok, ol, scores ? os : nullptr, n_new,
-                                uws, s));
-    DM_COUNT_LAUNCH(); merge::copy_edges_kernel<<<grid_for(capacity), 256, 0, s>>>(ok, ol, scores ? os : nullptr, n_new, keys, lens, scores);
-    DM_CUDA(cudaMemcpyAsync(n_dev, n_new, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    DM_TRY(prims::sort_unique(nk, perm, n_dev, capacity, b, 2 * b, sws, lens, scores, sentinel, ok, ol, scores ? os : nullptr,
+                              n_new, uws, keys, lens, scores, n_dev, s));
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

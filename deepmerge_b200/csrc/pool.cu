@@ -300,7 +300,7 @@ extern "C" int dm_csr_build(const int32_t* rop, int64_t n, int64_t R, int64_t* o
     DM_COUNT_LAUNCH(); pool::csr_keys_kernel<<<g, 256, 0, s>>>(rop, n, R, keys, vals, n_dev);
     // stable sort by region only (input is in ascending point id): low bits_for(R+1) bits
     const int b = bits_for(R + 1);
-    DM_TRY(prims::sort_pairs(keys, vals, n_dev, n, b, b, sws, s));
+    DM_TRY(prims::sort_pairs(keys, vals, n_dev, n, b, b, sws, s, false));   // runs beside the raster pass
     DM_COUNT_LAUNCH(); pool::csr_offsets_kernel<<<pool::grid_for((n > R ? n : R) + 1, 256, 8), 256, 0, s>>>(keys, vals, n, R, offsets, point_ids);
     DM_LAUNCH_CHECK();
     return DM_OK;

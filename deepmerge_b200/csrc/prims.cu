@@ -1,5 +1,7 @@
 // Scan / radix sort / run reduction (see prims.cuh).  Hand-written for sm_100a; no CUB.
 #include "prims.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace dm {
 namespace prims {
@@ -88,89 +90,106 @@ int scan_exclusive_u32(const uint32_t* in, uint32_t* out, const int64_t* n_dev, 
 }
 
 // ------------------------------------------------------------------------------------ //
-// LSD radix sort, 9-bit digits, 3 kernels per pass (tile histogram, offsets, scatter)
+// LSD radix sort, 9-bit digits.  Per pass: tile histograms, per-digit offsets over tiles, scatter.
+// Two drivers share the per-tile device code:
+//   * radix_sort_fused: ONE cooperative launch for the whole sort (and, optionally, the run
+//     reduction that follows it); persistent blocks walk their tiles and meet at grid barriers
+//     between the phases.  At the sizes of the graph stages (<= a few million pairs) a pass is
+//     launch/latency bound, so 12 + 6 launches collapse into one.
+//   * radix_hist / radix_offsets / radix_scatter: one launch per phase (no co-residency needed;
+//     used beside the raster kernel, which leaves no room for a co-resident grid).
+// Buffers written inside the fused kernel are read back with ld.global.cg (L2): L1 is not coherent
+// across blocks and `const __restrict__` loads could take the non-coherent path.
 // ------------------------------------------------------------------------------------ //
 constexpr int RADIX_BITS = 9;
 constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
 
 __device__ __forceinline__ unsigned digit_of(uint64_t key, int id_bits, int shift) {
     uint64_t ck = ((key >> 32) << id_bits) | (key & ((1ull << id_bits) - 1));
     return (unsigned)(ck >> shift) & (unsigned)(RADIX - 1);
 }
+__device__ __forceinline__ uint64_t ldcg64(const uint64_t* p) { return __ldcg((const unsigned long long*)p); }
+
+struct SortSmem {
+    uint32_t wcnt[SORT_WARPS][RADIX];   // per-warp digit counters (the first row doubles as the tile histogram)
+    uint32_t goff[RADIX];
+    uint32_t scan[SORT_THREADS / 32 + 1];
+};
 
 // hist is digit-major: hist[d * tiles_cap + tile], so that the per-digit scan over tiles is coalesced
-__global__ void __launch_bounds__(SORT_THREADS) radix_hist(const uint64_t* __restrict__ keys,
-                                                           const int64_t* __restrict__ n_dev, int id_bits, int shift,
-                                                           uint32_t* __restrict__ hist, int tiles_cap) {
-    const int64_t n = *n_dev;
-    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
-    if (base >= n) return;
-    __shared__ uint32_t h[RADIX];
+__device__ __forceinline__ void hist_tile(SortSmem& sm, const uint64_t* keys, int64_t n, int tile, int id_bits, int shift,
+                                          uint32_t* hist, int tiles_cap) {
+    uint32_t* h = sm.wcnt[0];
     for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) h[i] = 0;
     __syncthreads();
+    const int64_t base = (int64_t)tile * SORT_TILE;
+    uint64_t key[SORT_ITEMS];                              // all loads first: one round trip, not SORT_ITEMS
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
-        int64_t idx = base + i * SORT_THREADS + threadIdx.x;
-        if (idx < n) atomicAdd(&h[digit_of(keys[idx], id_bits, shift)], 1u);
+        const int64_t idx = base + i * SORT_THREADS + threadIdx.x;
+        key[i] = idx < n ? ldcg64(keys + idx) : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const int64_t idx = base + i * SORT_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&h[digit_of(key[i], id_bits, shift)], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) hist[(size_t)i * tiles_cap + blockIdx.x] = h[i];
+    for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) hist[(size_t)i * tiles_cap + tile] = h[i];
+    __syncthreads();
 }
 
 // One warp per digit: turns the per-tile counts of that digit into an exclusive prefix over tiles
 // (in place) and writes the digit's total to totals[d].  The digit bases (exclusive scan of the
 // totals) are computed by every scatter block itself.
-__global__ void __launch_bounds__(1024) radix_offsets(uint32_t* __restrict__ hist, const int64_t* __restrict__ n_dev,
-                                                      uint32_t* __restrict__ totals, int tiles_cap) {
-    const int64_t n = *n_dev;
-    const int tiles = (int)((n + SORT_TILE - 1) / SORT_TILE);
+__device__ __forceinline__ void offsets_digit(uint32_t* hist, uint32_t* totals, int d, int tiles, int tiles_cap) {
     const int lane = threadIdx.x & 31;
-    const int d = blockIdx.x * 32 + (threadIdx.x >> 5);
     uint32_t* row = hist + (size_t)d * tiles_cap;
     uint32_t carry = 0;
-    for (int t0 = 0; t0 < tiles; t0 += 32) {
-        const int t = t0 + lane;
-        const uint32_t c = t < tiles ? row[t] : 0;
-        uint32_t inc = c;
+    constexpr int UN = 8;                                  // 8 x 32 tiles in flight: the loads are the latency here
+    for (int t0 = 0; t0 < tiles; t0 += 32 * UN) {
+        uint32_t c[UN];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += v;
+        for (int j = 0; j < UN; ++j) {
+            const int t = t0 + 32 * j + lane;
+            c[j] = t < tiles ? __ldcg(row + t) : 0;
         }
-        if (t < tiles) row[t] = carry + inc - c;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+        for (int j = 0; j < UN; ++j) {
+            const int t = t0 + 32 * j + lane;
+            uint32_t inc = c[j];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (t < tiles) row[t] = carry + inc - c[j];
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
     }
     if (lane == 0) totals[d] = carry;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) radix_scatter(const uint64_t* __restrict__ kin,
-                                                              const uint32_t* __restrict__ vin,
-                                                              uint64_t* __restrict__ kout, uint32_t* __restrict__ vout,
-                                                              const int64_t* __restrict__ n_dev, int id_bits, int shift,
-                                                              const uint32_t* __restrict__ hist,
-                                                              const uint32_t* __restrict__ totals, int tiles_cap) {
-    const int64_t n = *n_dev;
-    const int64_t tile_base = (int64_t)blockIdx.x * SORT_TILE;
-    if (tile_base >= n) return;
-    constexpr int NW = SORT_THREADS / 32;
+__device__ __forceinline__ void scatter_tile(SortSmem& sm, const uint64_t* kin, const uint32_t* vin, uint64_t* kout,
+                                             uint32_t* vout, int64_t n, int tile, int id_bits, int shift,
+                                             const uint32_t* hist, const uint32_t* totals, int tiles_cap) {
     constexpr int PER = RADIX / SORT_THREADS;             // digits per thread in the block-wide steps
-    __shared__ uint32_t wcnt[NW][RADIX];
-    __shared__ uint32_t goff[RADIX];
-    __shared__ uint32_t sm_scan[SORT_THREADS / 32 + 1];
-    for (int i = threadIdx.x; i < NW * RADIX; i += SORT_THREADS) (&wcnt[0][0])[i] = 0;
+    const int64_t tile_base = (int64_t)tile * SORT_TILE;
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&sm.wcnt[0][0])[i] = 0;
     {   // digit base = exclusive scan of the digit totals (thread t owns digits [t*PER, (t+1)*PER))
         uint32_t t[PER], sum = 0;
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
-            t[k] = totals[threadIdx.x * PER + k];
+            t[k] = __ldcg(totals + threadIdx.x * PER + k);
             sum += t[k];
         }
         uint32_t tot;
-        uint32_t base = block_excl_scan<SORT_THREADS>(sum, sm_scan, tot);
+        uint32_t base = block_excl_scan<SORT_THREADS>(sum, sm.scan, tot);
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             const int d = threadIdx.x * PER + k;
-            goff[d] = base + hist[(size_t)d * tiles_cap + blockIdx.x];
+            sm.goff[d] = base + __ldcg(hist + (size_t)d * tiles_cap + tile);
             base += t[k];
         }
     }
@@ -178,12 +197,14 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter(const uint64_t* __
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t wbase = tile_base + (int64_t)warp * (32 * SORT_ITEMS);
     uint64_t key[SORT_ITEMS];
+    uint32_t val[SORT_ITEMS];
     uint32_t rank[SORT_ITEMS];
     unsigned dig[SORT_ITEMS];
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const int64_t idx = wbase + i * 32 + lane;
-        key[i] = idx < n ? kin[idx] : 0;
+        key[i] = idx < n ? ldcg64(kin + idx) : 0;
+        val[i] = (vin && idx < n) ? __ldcg(vin + idx) : 0;     // with the keys: one round trip for all loads
     }
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
@@ -198,8 +219,8 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter(const uint64_t* __
             const int leader = __ffs(peers) - 1;
             uint32_t pre = 0;
             if ((int)lane == leader) {
-                pre = wcnt[warp][dig[i]];
-                wcnt[warp][dig[i]] = pre + __popc(peers);
+                pre = sm.wcnt[warp][dig[i]];
+                sm.wcnt[warp][dig[i]] = pre + __popc(peers);
             }
             pre = __shfl_sync(peers, pre, leader);
             rank[i] = pre + __popc(peers & lanemask_lt());
@@ -210,9 +231,9 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter(const uint64_t* __
     for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) {   // exclusive prefix over warps, per digit
         uint32_t run = 0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            uint32_t c = wcnt[w][d];
-            wcnt[w][d] = run;
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            uint32_t c = sm.wcnt[w][d];
+            sm.wcnt[w][d] = run;
             run += c;
         }
     }
@@ -221,11 +242,37 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter(const uint64_t* __
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const int64_t idx = wbase + i * 32 + lane;
         if (idx < n) {
-            const uint32_t pos = goff[dig[i]] + wcnt[warp][dig[i]] + rank[i];
+            const uint32_t pos = sm.goff[dig[i]] + sm.wcnt[warp][dig[i]] + rank[i];
             kout[pos] = key[i];
-            if (vin) vout[pos] = vin[idx];
+            if (vin) vout[pos] = val[i];
         }
     }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) radix_hist(const uint64_t* keys, const int64_t* __restrict__ n_dev,
+                                                           int id_bits, int shift, uint32_t* hist, int tiles_cap) {
+    const int64_t n = *n_dev;
+    if ((int64_t)blockIdx.x * SORT_TILE >= n) return;
+    __shared__ SortSmem sm;
+    hist_tile(sm, keys, n, (int)blockIdx.x, id_bits, shift, hist, tiles_cap);
+}
+
+__global__ void __launch_bounds__(1024) radix_offsets(uint32_t* hist, const int64_t* __restrict__ n_dev, uint32_t* totals,
+                                                      int tiles_cap) {
+    const int64_t n = *n_dev;
+    const int tiles = (int)((n + SORT_TILE - 1) / SORT_TILE);
+    offsets_digit(hist, totals, blockIdx.x * 32 + (threadIdx.x >> 5), tiles, tiles_cap);
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) radix_scatter(const uint64_t* kin, const uint32_t* vin, uint64_t* kout,
+                                                              uint32_t* vout, const int64_t* __restrict__ n_dev, int id_bits,
+                                                              int shift, const uint32_t* hist, const uint32_t* totals,
+                                                              int tiles_cap) {
+    const int64_t n = *n_dev;
+    if ((int64_t)blockIdx.x * SORT_TILE >= n) return;
+    __shared__ SortSmem sm;
+    scatter_tile(sm, kin, vin, kout, vout, n, (int)blockIdx.x, id_bits, shift, hist, totals, tiles_cap);
 }
 
 __global__ void copy_pairs(const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout,
@@ -237,6 +284,179 @@ __global__ void copy_pairs(const uint64_t* __restrict__ kin, const uint32_t* __r
     }
 }
 
+// ---- the fused (single cooperative launch) driver ---------------------------------------
+
+struct FusedArgs {
+    uint64_t* k0; uint32_t* v0;          // the pairs (in place); v0 may be null
+    uint64_t* k1; uint32_t* v1;          // ping-pong buffers
+    const int64_t* n_dev; int64_t n_max; // n = min(*n_dev, n_max)
+    uint32_t* hist; uint32_t* totals;
+    unsigned* bar;                       // [0] arrivals (zeroed before the launch), [1] error flag
+    int id_bits, passes, tiles_cap;
+    // run reduction of the sorted pairs (do_unique): see unique_reduce
+    int do_unique;
+    const uint32_t* gather_lens;         // null: the sorted values are the lengths; else lengths / scores are
+    const float* gather_scores;          //       gathered through the sorted values (a permutation)
+    uint64_t sentinel;
+    uint64_t* out_keys; uint32_t* out_lens; float* out_scores; int64_t* n_out;
+    uint32_t* tile_heads;                // [tiles_cap]
+    // optional copy of the reduced list back over caller arrays (after one more barrier)
+    uint64_t* back_keys; uint32_t* back_lens; float* back_scores; int64_t* back_n;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All blocks of the (co-resident) grid meet here.  Arrivals only ever grow: barrier k completes at k * gridDim.x.
+// The wait is bounded: a grid that cannot meet becomes an error + trap, not a hung GPU.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
+    __syncthreads();
+    target += gridDim.x;
+    if (threadIdx.x == 0) {
+        // release / acquire at gpu scope; bar.sync on both sides extends the ordering to the whole block
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+        unsigned spins = 0;
+        while (ld_acquire_u32(bar) < target) {
+            if (++spins > (1u << 23)) {
+                atomicExch(bar + 1, 1u);
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SORT_THREADS, 3) radix_sort_fused(const FusedArgs A) {
+    __shared__ SortSmem sm;
+    const int64_t n = imin64(*A.n_dev, A.n_max);
+    const int tiles = (int)((n + SORT_TILE - 1) / SORT_TILE);
+    const int G = (int)gridDim.x;
+    unsigned target = 0;
+    uint64_t *ka = A.k0, *kb = A.k1;
+    uint32_t *va = A.v0, *vb = A.v0 ? A.v1 : nullptr;
+    for (int p = 0; p < A.passes; ++p) {
+        const int shift = RADIX_BITS * p;
+        for (int t = blockIdx.x; t < tiles; t += G) hist_tile(sm, ka, n, t, A.id_bits, shift, A.hist, A.tiles_cap);
+        grid_barrier(A.bar, target);
+        for (int d = blockIdx.x * SORT_WARPS + (threadIdx.x >> 5); d < RADIX; d += G * SORT_WARPS)
+            offsets_digit(A.hist, A.totals, d, tiles, A.tiles_cap);
+        grid_barrier(A.bar, target);
+        for (int t = blockIdx.x; t < tiles; t += G)
+            scatter_tile(sm, ka, va, kb, vb, n, t, A.id_bits, shift, A.hist, A.totals, A.tiles_cap);
+        grid_barrier(A.bar, target);
+        uint64_t* tk = ka; ka = kb; kb = tk;
+        uint32_t* tv = va; va = vb; vb = tv;
+    }
+    if (!A.do_unique) {
+        if (ka != A.k0) {                                  // odd number of passes: move the result home
+            for (int64_t i = (int64_t)blockIdx.x * SORT_THREADS + threadIdx.x; i < n; i += (int64_t)G * SORT_THREADS) {
+                A.k0[i] = ldcg64(ka + i);
+                if (va) A.v0[i] = __ldcg(va + i);
+            }
+        }
+        return;
+    }
+    // ---- run reduction: heads per tile -> (barrier) -> tile bases, in-tile scan, scatter + length sums ----
+    // blocked arrangement: thread t owns items [t*ITEMS, (t+1)*ITEMS) of its tile
+    for (int t = blockIdx.x; t < tiles; t += G) {
+        const int64_t base = (int64_t)t * SORT_TILE + (int64_t)threadIdx.x * SORT_ITEMS;
+        uint32_t heads = 0;
+        uint64_t prev = (base > 0 && base - 1 < n) ? ldcg64(ka + base - 1) : 0;
+        uint64_t key[SORT_ITEMS];
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i) key[i] = base + i < n ? ldcg64(ka + base + i) : 0;
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            const int64_t idx = base + i;
+            if (idx < n) {
+                heads += (key[i] != A.sentinel && (idx == 0 || key[i] != prev)) ? 1u : 0u;
+                prev = key[i];
+                A.out_lens[idx] = 0;
+            }
+        }
+        uint32_t total;
+        block_excl_scan<SORT_THREADS>(heads, sm.scan, total);
+        if (threadIdx.x == 0) A.tile_heads[t] = total;
+    }
+    grid_barrier(A.bar, target);
+    if (blockIdx.x == 0) {                                 // number of runs = heads in all tiles
+        uint32_t part = 0, n_runs;
+        for (int u = threadIdx.x; u < tiles; u += SORT_THREADS) part += __ldcg(A.tile_heads + u);
+        block_excl_scan<SORT_THREADS>(part, sm.scan, n_runs);
+        if (threadIdx.x == 0) *A.n_out = (int64_t)n_runs;
+    }
+    for (int t = blockIdx.x; t < tiles; t += G) {
+        uint32_t part = 0, tile_base;                      // heads in the tiles before this one
+        for (int u = threadIdx.x; u < t; u += SORT_THREADS) part += __ldcg(A.tile_heads + u);
+        block_excl_scan<SORT_THREADS>(part, sm.scan, tile_base);
+        const int64_t base = (int64_t)t * SORT_TILE + (int64_t)threadIdx.x * SORT_ITEMS;
+        uint64_t key[SORT_ITEMS];
+        uint32_t flag[SORT_ITEMS];
+        uint32_t heads = 0;
+        uint64_t prev = (base > 0 && base - 1 < n) ? ldcg64(ka + base - 1) : 0;
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            const int64_t idx = base + i;
+            key[i] = idx < n ? ldcg64(ka + idx) : A.sentinel;
+            flag[i] = (idx < n && key[i] != A.sentinel && (idx == 0 || key[i] != prev)) ? 1u : 0u;
+            heads += flag[i];
+            prev = key[i];
+        }
+        uint32_t src[SORT_ITEMS], len[SORT_ITEMS];          // every load before the first store (they may alias)
+        float sc[SORT_ITEMS];
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            const int64_t idx = base + i;
+            const bool live = idx < n && key[i] != A.sentinel;
+            const uint32_t v = (live && va) ? __ldcg(va + idx) : 0u;
+            src[i] = A.gather_lens ? v : (uint32_t)idx;
+            len[i] = v;
+        }
+        if (A.gather_lens) {
+#pragma unroll
+            for (int i = 0; i < SORT_ITEMS; ++i) {
+                const bool live = base + i < n && key[i] != A.sentinel;
+                len[i] = live ? A.gather_lens[src[i]] : 0u;
+                sc[i] = (live && flag[i] && A.gather_scores) ? A.gather_scores[src[i]] : 0.f;
+            }
+        }
+        uint32_t total;
+        uint32_t excl = block_excl_scan<SORT_THREADS>(heads, sm.scan, total) + tile_base;
+        uint32_t acc = 0, acc_run = 0xffffffffu;            // lengths of one run are summed locally first
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            const int64_t idx = base + i;
+            if (idx < n && key[i] != A.sentinel) {
+                const uint32_t run = excl + flag[i] - 1;
+                if (flag[i]) {
+                    A.out_keys[run] = key[i];
+                    if (A.gather_scores) A.out_scores[run] = sc[i];
+                }
+                if (run != acc_run) {
+                    if (acc) atomicAdd(&A.out_lens[acc_run], acc);
+                    acc = 0;
+                    acc_run = run;
+                }
+                acc += len[i];
+            }
+            excl += flag[i];
+        }
+        if (acc) atomicAdd(&A.out_lens[acc_run], acc);
+    }
+    if (!A.back_keys) return;
+    grid_barrier(A.bar, target);
+    const int64_t m = (int64_t)__ldcg((const long long*)A.n_out);
+    for (int64_t i = (int64_t)blockIdx.x * SORT_THREADS + threadIdx.x; i < m; i += (int64_t)G * SORT_THREADS) {
+        A.back_keys[i] = ldcg64(A.out_keys + i);
+        A.back_lens[i] = __ldcg(A.out_lens + i);
+        if (A.back_scores && A.out_scores) A.back_scores[i] = __ldcg(A.out_scores + i);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && A.back_n) *A.back_n = m;
+}
+
 size_t sort_ws_bytes(int64_t cap) {
     if (cap < 1) cap = 1;
     size_t b = 0;
@@ -244,27 +464,97 @@ size_t sort_ws_bytes(int64_t cap) {
     b += align_up((size_t)cap * sizeof(uint32_t), 256);
     b += align_up((size_t)ceil_div(cap, SORT_TILE) * RADIX * sizeof(uint32_t), 256);
     b += align_up(RADIX * sizeof(uint32_t), 256);
+    b += 256;                                              // grid barrier words of the fused kernel
     return b;
 }
 
+namespace {
+struct SortWs {
+    uint64_t* k2;
+    uint32_t* v2;
+    uint32_t* hist;
+    uint32_t* totals;
+    unsigned* bar;
+    unsigned tiles;
+};
+SortWs carve_sort_ws(void* ws, int64_t cap) {
+    Carver c(ws);
+    SortWs w;
+    w.k2 = c.take<uint64_t>(cap);
+    w.v2 = c.take<uint32_t>(cap);
+    w.tiles = (unsigned)ceil_div(cap, SORT_TILE);
+    w.hist = c.take<uint32_t>((size_t)w.tiles * RADIX);
+    w.totals = c.take<uint32_t>(RADIX);
+    w.bar = c.take<unsigned>(2);
+    return w;
+}
+
+// DM_SORT_FUSED: 0 = one launch per phase everywhere, 1 = fused kernel for the edge sorts, 2 (default) = also for the
+// member sort of dm_merge_apply, which runs on a side stream beside the edge re-keying.
+int fused_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("DM_SORT_FUSED");
+        mode = (e && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 2;
+    }
+    return mode;
+}
+
+// Blocks of the fused kernel that are co-resident on this device (0: cooperative launch unsupported).
+int fused_grid_limit() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev != cached_dev) {
+        int coop = 0, per_sm = 0;
+        cached = 0;
+        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_sort_fused, SORT_THREADS, 0) == cudaSuccess)
+            cached = (per_sm < 2 ? per_sm : 2) * num_sms();     // measured: a third block per SM costs more in the
+                                                                // barriers than it saves in the phases
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+int launch_fused(FusedArgs& A, int64_t cap, cudaStream_t s) {
+    const int limit = fused_grid_limit();
+    if (limit <= 0) return DM_ERR_UNSUPPORTED;
+    const int grid = (int)imax64(1, imin64(ceil_div(cap, SORT_TILE), limit));
+    DM_CUDA(cudaMemsetAsync(A.bar, 0, 2 * sizeof(unsigned), s));
+    void* args[] = {(void*)&A};
+    DM_COUNT_LAUNCH();
+    DM_CUDA(cudaLaunchCooperativeKernel((const void*)radix_sort_fused, dim3(grid), dim3(SORT_THREADS), args, 0, s));
+    return DM_OK;
+}
+}  // namespace
+
+int sort_fused_mode() { return fused_mode(); }
+bool sort_fused_available() { return fused_mode() != 0 && fused_grid_limit() > 0; }
+
 int sort_pairs(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t cap, int id_bits, int key_bits, void* ws,
-               cudaStream_t s) {
+               cudaStream_t s, bool allow_fused) {
     if (cap <= 0) return DM_OK;
     if (id_bits < 1 || id_bits > 32 || key_bits < 1 || key_bits > 2 * id_bits) return DM_ERR_BAD_ARG;
-    Carver c(ws);
-    uint64_t* k2 = c.take<uint64_t>(cap);
-    uint32_t* v2 = c.take<uint32_t>(cap);
-    const unsigned tiles = (unsigned)ceil_div(cap, SORT_TILE);
-    uint32_t* hist = c.take<uint32_t>((size_t)tiles * RADIX);
-    uint32_t* totals = c.take<uint32_t>(RADIX);
+    const SortWs w = carve_sort_ws(ws, cap);
     const int passes = (key_bits + RADIX_BITS - 1) / RADIX_BITS;
-    uint64_t *ka = keys, *kb = k2;
-    uint32_t *va = vals, *vb = vals ? v2 : nullptr;
+    if (allow_fused && sort_fused_available()) {
+        FusedArgs A;
+        memset(&A, 0, sizeof(A));
+        A.k0 = keys; A.v0 = vals; A.k1 = w.k2; A.v1 = w.v2;
+        A.n_dev = n_dev; A.n_max = cap;
+        A.hist = w.hist; A.totals = w.totals; A.bar = w.bar;
+        A.id_bits = id_bits; A.passes = passes; A.tiles_cap = (int)w.tiles;
+        return launch_fused(A, cap, s);
+    }
+    const unsigned tiles = w.tiles;
+    uint64_t *ka = keys, *kb = w.k2;
+    uint32_t *va = vals, *vb = vals ? w.v2 : nullptr;
     for (int p = 0; p < passes; ++p) {
-        DM_COUNT_LAUNCH(); radix_hist<<<tiles, SORT_THREADS, 0, s>>>(ka, n_dev, id_bits, RADIX_BITS * p, hist, (int)tiles);
-        DM_COUNT_LAUNCH(); radix_offsets<<<RADIX / 32, 1024, 0, s>>>(hist, n_dev, totals, (int)tiles);
-        DM_COUNT_LAUNCH(); radix_scatter<<<tiles, SORT_THREADS, 0, s>>>(ka, va, kb, vb, n_dev, id_bits, RADIX_BITS * p, hist, totals,
-                                                    (int)tiles);
+        DM_COUNT_LAUNCH(); radix_hist<<<tiles, SORT_THREADS, 0, s>>>(ka, n_dev, id_bits, RADIX_BITS * p, w.hist, (int)tiles);
+        DM_COUNT_LAUNCH(); radix_offsets<<<RADIX / 32, 1024, 0, s>>>(w.hist, n_dev, w.totals, (int)tiles);
+        DM_COUNT_LAUNCH(); radix_scatter<<<tiles, SORT_THREADS, 0, s>>>(ka, va, kb, vb, n_dev, id_bits, RADIX_BITS * p, w.hist,
+                                                    w.totals, (int)tiles);
         uint64_t* tk = ka; ka = kb; kb = tk;
         uint32_t* tv = va; va = vb; vb = tv;
     }
@@ -309,6 +599,17 @@ __global__ void unique_scatter(const uint64_t* __restrict__ keys, const uint32_t
     }
 }
 
+__global__ void copy_runs(const uint64_t* __restrict__ k, const uint32_t* __restrict__ l, const float* __restrict__ sc,
+                          const int64_t* __restrict__ n_dev, uint64_t* __restrict__ ko, uint32_t* __restrict__ lo,
+                          float* __restrict__ so) {
+    const int64_t n = *n_dev;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        ko[e] = k[e];
+        lo[e] = l[e];
+        if (so && sc) so[e] = sc[e];
+    }
+}
+
 size_t unique_ws_bytes(int64_t cap) {
     if (cap < 1) cap = 1;
     return 2 * align_up((size_t)cap * sizeof(uint32_t), 256) + scan_ws_bytes(cap);
@@ -332,6 +633,45 @@ int unique_reduce(const uint64_t* keys, const uint32_t* perm, const uint32_t* le
     DM_COUNT_LAUNCH(); unique_scatter<<<g, 256, 0, s>>>(keys, perm, lens_in, scores_in, n_dev, sentinel, flags, excl, out_keys, out_lens,
                                      out_scores);
     DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+int sort_unique(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t cap, int id_bits, int key_bits, void* sort_ws,
+                const uint32_t* gather_lens, const float* gather_scores, uint64_t sentinel, uint64_t* out_keys,
+                uint32_t* out_lens, float* out_scores, int64_t* n_out_dev, void* unique_ws, uint64_t* back_keys,
+                uint32_t* back_lens, float* back_scores, int64_t* back_n, cudaStream_t s) {
+    if (cap <= 0) {
+        DM_CUDA(cudaMemsetAsync(n_out_dev, 0, sizeof(int64_t), s));
+        if (back_n) DM_CUDA(cudaMemsetAsync(back_n, 0, sizeof(int64_t), s));
+        return DM_OK;
+    }
+    if (!vals || id_bits < 1 || id_bits > 32 || key_bits < 1 || key_bits > 2 * id_bits) return DM_ERR_BAD_ARG;
+    if (sort_fused_available()) {
+        const SortWs w = carve_sort_ws(sort_ws, cap);
+        FusedArgs A;
+        memset(&A, 0, sizeof(A));
+        A.k0 = keys; A.v0 = vals; A.k1 = w.k2; A.v1 = w.v2;
+        A.n_dev = n_dev; A.n_max = cap;
+        A.hist = w.hist; A.totals = w.totals; A.bar = w.bar;
+        A.id_bits = id_bits; A.passes = (key_bits + RADIX_BITS - 1) / RADIX_BITS; A.tiles_cap = (int)w.tiles;
+        A.do_unique = 1;
+        A.gather_lens = gather_lens; A.gather_scores = gather_lens ? gather_scores : nullptr;
+        A.sentinel = sentinel;
+        A.out_keys = out_keys; A.out_lens = out_lens; A.out_scores = out_scores; A.n_out = n_out_dev;
+        A.tile_heads = (uint32_t*)unique_ws;               // unique_ws_bytes(cap) >= tiles words
+        A.back_keys = back_keys; A.back_lens = back_lens; A.back_scores = back_scores; A.back_n = back_n;
+        return launch_fused(A, cap, s);
+    }
+    DM_TRY(sort_pairs(keys, vals, n_dev, cap, id_bits, key_bits, sort_ws, s, false));
+    DM_TRY(unique_reduce(keys, gather_lens ? vals : nullptr, gather_lens ? gather_lens : vals,
+                         gather_lens ? gather_scores : nullptr, n_dev, cap, sentinel, out_keys, out_lens, out_scores,
+                         n_out_dev, unique_ws, s));
+    if (back_keys) {
+        const unsigned g = (unsigned)imax64(1, imin64(ceil_div(cap, 256), (int64_t)num_sms() * 8));
+        DM_COUNT_LAUNCH(); copy_runs<<<g, 256, 0, s>>>(out_keys, out_lens, out_scores, n_out_dev, back_keys, back_lens, back_scores);
+        if (back_n) DM_CUDA(cudaMemcpyAsync(back_n, n_out_dev, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+        DM_LAUNCH_CHECK();
+    }
     return DM_OK;
 }
 

@@ -23,8 +23,12 @@ size_t sort_ws_bytes(int64_t cap);
 // Stable sort of (keys, vals) in place by the low key_bits bits of the compacted key
 // ((hi32 << id_bits) | lo32); both 32-bit halves of every key must be < 2^id_bits.
 // key_bits = 2*id_bits sorts by (hi, lo); key_bits = id_bits sorts by lo only.  vals may be null.
+// allow_fused: the whole sort may run as ONE cooperative launch (persistent blocks + grid barriers); callers that
+// sort beside a kernel filling every SM (the pooling chain beside the raster pass) pass false.
 int sort_pairs(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t cap, int id_bits, int key_bits,
-               void* ws, cudaStream_t s);
+               void* ws, cudaStream_t s, bool allow_fused = true);
+bool sort_fused_available();
+int sort_fused_mode();   // DM_SORT_FUSED: 0 off, 1 edge sorts, 2 (default) also the member sort of dm_merge_apply
 
 size_t unique_ws_bytes(int64_t cap);
 // keys sorted.  For every run of equal keys (runs of `sentinel` are dropped):
@@ -33,6 +37,15 @@ size_t unique_ws_bytes(int64_t cap);
 int unique_reduce(const uint64_t* keys, const uint32_t* perm, const uint32_t* lens_in, const float* scores_in,
                   const int64_t* n_dev, int64_t cap, uint64_t sentinel, uint64_t* out_keys, uint32_t* out_lens,
                   float* out_scores, int64_t* n_out_dev, void* ws, cudaStream_t s);
+
+// sort_pairs + unique_reduce (+ an optional copy of the reduced list over back_keys / back_lens / back_scores and
+// its length to back_n) -- one launch when the fused kernel is available.  n = min(*n_dev, cap) pairs are read.
+// gather_lens == null: the (sorted) values are the lengths.  Otherwise the values are a permutation and lengths /
+// scores are gathered through it (gather_lens[vals[i]], gather_scores[vals[i]]).
+int sort_unique(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t cap, int id_bits, int key_bits, void* sort_ws,
+                const uint32_t* gather_lens, const float* gather_scores, uint64_t sentinel, uint64_t* out_keys,
+                uint32_t* out_lens, float* out_scores, int64_t* n_out_dev, void* unique_ws, uint64_t* back_keys,
+                uint32_t* back_lens, float* back_scores, int64_t* back_n, cudaStream_t s);
 
 // ---- device helpers -------------------------------------------------------------------
 

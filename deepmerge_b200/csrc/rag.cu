@@ -954,14 +954,6 @@ static bool make_map_2d(CUtensorMap* m, const void* base, uint64_t dim0, uint64_
 __global__ void clamp_count_kernel(const int64_t* raw, int64_t capacity, int64_t* out) {
     *out = *raw < capacity ? *raw : capacity;
 }
-__global__ void copy_back_kernel(const uint64_t* __restrict__ k, const uint32_t* __restrict__ l,
-                                 const int64_t* __restrict__ n_dev, uint64_t* __restrict__ ko, uint32_t* __restrict__ lo) {
-    const int64_t n = *n_dev;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        ko[e] = k[e];
-        lo[e] = l[e];
-    }
-}
 
 template <typename CF>
 static int launch(const Params& Pin, bool allow_tma, cudaStream_t s) {
@@ -1107,12 +1099,15 @@ extern "C" int dm_rag_finish(uint64_t* edge_keys, uint32_t* boundary_len, int64_
     if (ws_bytes < dm_rag_workspace_bytes(capacity)) return DM_ERR_WORKSPACE;
     cudaStream_t s = S(stream);
     RagWs w = carve_rag_ws(ws, capacity);
-    // n_raw = min(raw entries, capacity): what actually sits in the raw list
-    DM_COUNT_LAUNCH(); rag::clamp_count_kernel<<<1, 1, 0, s>>>(counts + 1, capacity, w.n_raw);
     const int b = bits_for(n_regions);
-    DM_TRY(prims::sort_pairs(w.raw_keys, w.raw_cnt, w.n_raw, capacity, b, 2 * b, w.sws, s));
-    DM_TRY(prims::unique_reduce(w.raw_keys, nullptr, w.raw_cnt, nullptr, w.n_raw, capacity, ~0ull, edge_keys, boundary_len,
-                                nullptr, counts, w.uws, s));
+    const int64_t* n_raw = counts + 1;                      // the fused kernel clamps to capacity itself
+    if (!prims::sort_fused_available()) {
+        // n_raw = min(raw entries, capacity): what actually sits in the raw list
+        DM_COUNT_LAUNCH(); rag::clamp_count_kernel<<<1, 1, 0, s>>>(counts + 1, capacity, w.n_raw);
+        n_raw = w.n_raw;
+    }
+    DM_TRY(prims::sort_unique(w.raw_keys, w.raw_cnt, n_raw, capacity, b, 2 * b, w.sws, nullptr, nullptr, ~0ull, edge_keys,
+                              boundary_len, nullptr, counts, w.uws, nullptr, nullptr, nullptr, nullptr, s));
     DM_LAUNCH_CHECK();
     return DM_OK;
 }
@@ -1202,11 +1197,8 @@ extern "C" int dm_edges_sort_unique(uint64_t* keys, uint32_t* lens, const int64_
     void* sws = c.take<char>(prims::sort_ws_bytes(capacity));
     void* uws = c.take<char>(prims::unique_ws_bytes(capacity));
     const int b = bits_for(n_regions);
-    DM_TRY(prims::sort_pairs(keys, lens, n_in, capacity, b, 2 * b, sws, s));
-    DM_TRY(prims::unique_reduce(keys, nullptr, lens, nullptr, n_in, capacity, ~0ull, ok, ol, nullptr, n_new, uws, s));
-    DM_COUNT_LAUNCH(); rag::copy_back_kernel<<<(unsigned)imax64(1, imin64(ceil_div(capacity, 256), (int64_t)num_sms() * 8)), 256, 0, s>>>(
-        ok, ol, n_new, keys, lens);
-    DM_CUDA(cudaMemcpyAsync(n_out, n_new, sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+    DM_TRY(prims::sort_unique(keys, lens, n_in, capacity, b, 2 * b, sws, nullptr, nullptr, ~0ull, ok, ol, nullptr, n_new, uws,
+                              keys, lens, nullptr, n_out, s));
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

@@ -497,6 +497,7 @@ class MergeEngine:
                 cur = torch.cuda.current_stream(self.dev)
                 self.side.wait_stream(cur)
                 with torch.cuda.stream(self.side):
+                    self._merge_init()
                     self._pool(labels, xs, ys, region_of_point, feats)
                     self._mean_all()
                 self._rag(labels, image, rows_own, top_border, bottom_border)
@@ -508,6 +509,8 @@ class MergeEngine:
                     self.cap = int(ov.args[0]) + 1024
                     self._alloc()
             if relabel:
+                # launched after the loop's last read-back, not gated behind the selection: in a stream of scenes the host
+                # prepares the next scene's launches while this kernel runs (measured: a gated launch costs 90 us / step)
                 own = labels.shape[0] if rows_own is None else rows_own
                 self.L.check(self.L.dm_relabel(_p(labels), own, self.W, labels.stride(0), _p(self.parent), self.R,
                                                _p(self.out), self.W, _stream()), "dm_relabel")
@@ -530,14 +533,21 @@ class MergeEngine:
             L.check(L.dm_score_mlp_bf16(_p(self.mean), D, _p(self.keys), _p(n_edges), cap, _p(mlp.blob), mlp.in_features,
                                         mlp.hidden, mlp.n_out, _p(self.logits), None, s), "dm_score_mlp_bf16")
 
+    def _merge_init(self):
+        """parent = identity, everything alive, round counters zero (run() does this beside the raster pass)."""
+        self.parent.copy_(self.iota)
+        self.alive.fill_(1)
+        self.counts[5:8].zero_()
+        self._init_fresh = True
+
     def _merge_loop(self, tau, max_rounds, mlp=None):
         L, s, R, D, cap = self.L, _stream(), self.R, self.D, self.cap
         n_edges = self.counts[0:1]
         if mlp is not None and mlp.in_features != 2 * D:
             raise ValueError("the pair-MLP takes concat(mean[lo], mean[hi]): in_features must be 2 D")
-        self.parent.copy_(self.iota)
-        self.alive.fill_(1)
-        self.counts[5:8].zero_()
+        if not getattr(self, "_init_fresh", False):
+            self._merge_init()
+        self._init_fresh = False
         if not getattr(self, "_means_fresh", False):      # run() computes them on the side stream right after the pooling
             self._mean_all()
         self._means_fresh = False

@@ -24,7 +24,7 @@ def keys_np(t):
 # ------------------------------------------------------------------------------------------
 # primitives
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,R", [(0, 10), (1, 2), (777, 5), (5000, 70000), (300000, 1 << 20), (70000, 3)])
+@pytest.mark.parametrize("n,R", [(0, 10), (1, 2), (777, 5), (5000, 70000), (300000, 1 << 20), (70000, 3), (2500000, 1 << 14)])
 def test_sort_edges(cuda, n, R):
     import torch
     from deepmerge_b200._lib import lib
@@ -47,6 +47,37 @@ def test_sort_edges(cuda, n, R):
     order = np.argsort(keys, kind="stable")
     assert np.array_equal(keys_np(k[:n]), keys[order])
     assert np.array_equal(v[:n].cpu().numpy().view(np.uint32), vals[order])      # stable
+
+
+@pytest.mark.parametrize("n,R", [(0, 10), (1, 2), (2048, 3), (5000, 40), (300000, 700), (2500000, 2500)])
+def test_edges_sort_unique(cuda, n, R):
+    """Sort + run reduction (one cooperative launch when available): unique keys ascending, lengths summed."""
+    import torch
+    from deepmerge_b200._lib import lib
+    L = lib()
+    rng = np.random.default_rng(7 * n + R)
+    lo = rng.integers(0, R, n)
+    hi = rng.integers(0, R, n)
+    keys = (lo.astype(np.uint64) << np.uint64(32)) | hi.astype(np.uint64)
+    lens = rng.integers(1, 1000, n).astype(np.uint32)
+    cap = n + 33
+    k = torch.full((cap,), -1, dtype=torch.int64, device=cuda)
+    v = torch.full((cap,), 12345, dtype=torch.int32, device=cuda)
+    k[:n] = T(keys.view(np.int64), cuda)
+    v[:n] = T(lens.view(np.int32), cuda)
+    nd = torch.tensor([n], dtype=torch.int64, device=cuda)
+    nout = torch.full((1,), -1, dtype=torch.int64, device=cuda)
+    wsb = L.dm_edges_unique_workspace_bytes(cap)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=cuda)
+    L.check(L.dm_edges_sort_unique(k.data_ptr(), v.data_ptr(), nd.data_ptr(), cap, R, nout.data_ptr(), ws.data_ptr(), wsb,
+                                   None), "sort_unique")
+    torch.cuda.synchronize()
+    uk, inv = np.unique(keys, return_inverse=True)
+    want = np.bincount(inv, weights=lens.astype(np.float64), minlength=len(uk)).astype(np.uint64)
+    m = int(nout.item())
+    assert m == len(uk)
+    assert np.array_equal(keys_np(k[:m]), uk)
+    assert np.array_equal(v[:m].cpu().numpy().view(np.uint32).astype(np.uint64), want)
 
 
 @pytest.mark.parametrize("n", [0, 1, 2047, 2048, 2049, 100000, 3000000])
