@@ -67,3 +67,112 @@ def pool_and_score(store, point_id_fields, left_ids, right_ids):
     keys = (torch.minimum(left, right) << 32) | torch.maximum(left, right)
     simi = score_l2(mean, keys, n2)
     return mean.cpu().numpy(), simi.cpu().numpy().astype(np.float64)
+
+
+class FeatureIO:
+    """The feature-store half of the reference's FeatureIO (ExtractFeatures.py:88-116): the HDF5 dataset
+    "dataset" [N, D] float32 that `extract_features` appends to and `test_for_shp` reads row by row.
+    h5py is used when it is installed; a `.npy` file with the same [N, D] array is accepted as well
+    (h5py is not part of this image).  The network half (`extract_features`) is out of scope here."""
+
+    def __init__(self, net=None, checkpoint_path=None):
+        self.net, self.checkpoint_path = net, checkpoint_path
+        self.h5py_file = None
+        self.dataset = None
+
+    def save_h5(self, h5f, data, dataset_name="dataset"):
+        """Append rows to the resizable dataset (created on first use), ExtractFeatures.py:88-101."""
+        shape = list(data.shape)
+        if dataset_name not in h5f:
+            shape[0] = None
+            h5f.create_dataset(dataset_name, data=data, maxshape=tuple(shape), chunks=True)
+            return
+        ds = h5f[dataset_name]
+        old = ds.shape[0]
+        shape[0] = old + data.shape[0]
+        ds.resize(tuple(shape))
+        ds[old:shape[0]] = data
+
+    def ReadFeatures(self, h5_file_path):
+        if str(h5_file_path).lower().endswith(".npy"):
+            self.dataset = np.load(h5_file_path, mmap_mode="r")
+            return
+        try:
+            import h5py
+        except ImportError as e:
+            raise RuntimeError("h5py is not installed: pass a .npy feature store or install h5py") from e
+        self.h5py_file = h5py.File(h5_file_path, "r")
+        self.dataset = self.h5py_file["dataset"]
+
+    def GetFeaturesByID(self, idx):
+        if idx >= len(self.dataset):
+            raise IndexError("index error!")                       # (the reference's `raise("index error!")` is a TypeError)
+        return np.asarray(self.dataset[idx])
+
+    def Close(self):
+        if self.h5py_file is not None:
+            self.h5py_file.close()
+            self.h5py_file = None
+
+
+def score_layers(store, polygon_layer, line_layer, scorer=None):
+    """test_for_shp's loop (ExtractFeatures.py:164-222) for EVERY line of `line_layer` (the reference `break`s
+    after the first): pool each polygon's `PointID` rows of `store`, score every LEFT_FID / RIGHT_FID pair with
+    the Euclidean distance and write it to the line attribute `simi` (created as OFTReal when missing).
+    Layers are OGR layers or deepmerge_b200.shapefile.ShapefileLayer objects.  -> (fids, left, right, simi).
+    `scorer(store, point_id_fields, left, right) -> (means, simi)` defaults to the GPU path `pool_and_score`."""
+    from . import shapefile
+    scorer = pool_and_score if scorer is None else scorer
+    fids, left, right = [], [], []
+    if isinstance(line_layer, shapefile.ShapefileLayer):            # whole columns at once
+        t = line_layer.table
+        l, r = t.column_int("LEFT_FID"), t.column_int("RIGHT_FID")
+        keep = (l != -1) & (r != -1) & ~t.deleted
+        fids, left, right = np.nonzero(keep)[0].tolist(), l[keep].tolist(), r[keep].tolist()
+    else:
+        line_layer.ResetReading()
+        f = line_layer.GetNextFeature()
+        while f is not None:
+            a, b = int(f.GetField("LEFT_FID")), int(f.GetField("RIGHT_FID"))
+            if a != -1 and b != -1:
+                fids.append(int(f.GetFID()))
+                left.append(a)
+                right.append(b)
+            f = line_layer.GetNextFeature()
+    if isinstance(polygon_layer, shapefile.ShapefileLayer):
+        point_ids = polygon_layer.table.column_str("PointID")
+    else:
+        point_ids = []
+        for i in range(polygon_layer.GetFeatureCount()):
+            v = polygon_layer.GetFeature(i).GetField("PointID")
+            point_ids.append("" if v is None else str(v))
+    _, simi = scorer(np.asarray(store), point_ids, left, right)
+    if line_layer.GetLayerDefn().GetFieldIndex("simi") < 0:
+        try:
+            from osgeo import ogr
+            defn = ogr.FieldDefn("simi", ogr.OFTReal)
+        except ImportError:
+            defn = shapefile.FieldDefn("simi", shapefile.OFTReal)
+        line_layer.CreateField(defn, 1)
+    if isinstance(line_layer, shapefile.ShapefileLayer):
+        line_layer.table.set_column("simi", np.asarray(simi, np.float64), rows=fids)
+        line_layer.table.flush()
+    else:
+        for fid, v in zip(fids, simi):
+            feat = line_layer.GetFeature(fid)
+            feat.SetField("simi", float(v))
+            line_layer.SetFeature(feat)
+    return np.asarray(fids, np.int64), np.asarray(left, np.int64), np.asarray(right, np.int64), np.asarray(simi, np.float64)
+
+
+def test_for_shp(featureIO, image_path=None, polygon_path=None, polyline_path=None, point_path=None):
+    """The reference's test_for_shp(featureIO) (ExtractFeatures.py:150-225) with its hard-coded paths as
+    arguments, every edge scored (no `break`), pooling + scoring on the GPU.  Returns 0 like the reference."""
+    from .MyUtils2 import PolygonConnectPointDataset
+    data_set = PolygonConnectPointDataset(image_path, polygon_path, polyline_path, point_path)
+    store = featureIO.dataset if getattr(featureIO, "dataset", None) is not None else featureIO
+    score_layers(store, data_set.polygon_layer, data_set.line_layer)
+    return 0
+
+
+test_for_shp.__test__ = False      # a reference-named entry point, not a pytest test

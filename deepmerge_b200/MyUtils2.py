@@ -2,10 +2,10 @@
 
 PolygonConnectPointDataset (MyUtils2.py:128-209) iterates the polyline layer of lines.shp and
 keeps [line_fid, tile_name, LEFT_FID, RIGHT_FID] for every feature whose two ids are not -1
-(:184-186).  GDAL/OGR is not part of this image, so the class takes already-opened layer
-objects (anything with ResetReading / GetNextFeature / GetField / GetFID, i.e. real OGR layers
-or the in-memory stand-ins used by the tests) next to the reference's path arguments; with
-osgeo importable it opens the paths exactly like the reference.  `edge_keys()` hands the list
+(:184-186).  With osgeo importable it opens the paths exactly like the reference; without it
+(this image) the shapefiles are opened by deepmerge_b200.shapefile, a pure-Python reader of the
+.dbf / .shp parts this path touches.  Already-opened layer objects (anything with ResetReading /
+GetNextFeature / GetField / GetFID) can be passed instead of paths.  `edge_keys()` hands the list
 to the GPU path as packed (min,max) keys.
 """
 from __future__ import annotations
@@ -30,8 +30,8 @@ class PolygonConnectPointDataset:
     def _open_with_ogr(self):
         try:
             from osgeo import gdal, ogr
-        except ImportError as e:
-            raise ValueError("Can not open {0}".format(self.polyline_path)) from e
+        except ImportError:
+            return self._open_without_gdal()
         drv = ogr.GetDriverByName("ESRI Shapefile")
         for attr, path in (("polygon", self.polygon_path), ("point", self.point_path), ("line", self.polyline_path)):
             ds = drv.Open(path, 1)
@@ -42,6 +42,20 @@ class PolygonConnectPointDataset:
         self.img_dataset = gdal.Open(self.image_path, gdal.GA_ReadOnly)
         if self.img_dataset is None:
             raise ValueError("Can not open {0}".format(self.image_path))
+
+    def _open_without_gdal(self):
+        """osgeo is not installed: the attribute tables (and point coordinates) are read by the pure-Python
+        adaptor deepmerge_b200.shapefile, which offers the OGR calls this path makes.  The image is only used for
+        its band count here and stays unopened (pass img_dataset= if a GDAL-like raster object is at hand)."""
+        from . import shapefile
+        for attr, path in (("polygon", self.polygon_path), ("point", self.point_path), ("line", self.polyline_path)):
+            ds = shapefile.Open(path, 1) if path else None
+            if ds is None:
+                if attr == "line" or path:
+                    raise ValueError("Can not open {0}".format(path))
+                continue
+            setattr(self, attr + "_dataset", ds)
+            setattr(self, attr + "_layer", ds.GetLayer(0))
 
     def __len__(self):
         return len(self.data)

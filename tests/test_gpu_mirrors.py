@@ -91,3 +91,27 @@ def test_cut_windows_matches_reference_cutter(cuda, golden_dir):
     for k in range(64):
         win = m.calculate_left_top_point_and_size(int(xs[k]), int(ys[k]), 9)
         assert np.array_equal(got[k], m.cut_image(g["arr"], win))
+
+
+def test_test_for_shp_on_real_shapefiles(cuda, golden_dir, tmp_path, capsys):
+    """The reference's test_for_shp (ExtractFeatures.py:150-225) end to end on files on disk: attribute tables read
+    without GDAL, pooling + scoring on the GPU, `simi` written back as an OFTReal attribute of every kept line."""
+    from deepmerge_b200 import shapefile
+    from deepmerge_b200.ExtractFeatures import FeatureIO, test_for_shp
+    p = np.load(os.path.join(golden_dir, "pool_score.npz"))
+    d = tmp_path / "tile"
+    d.mkdir()
+    left, right = p["left"].copy(), p["right"].copy()
+    right[7] = -1
+    shapefile.write_dbf(str(tmp_path / "tile.dbf"), [("PointID", "C", 60, 0)], {"PointID": list(p["fields"])})
+    shapefile.write_dbf(str(d / "lines.dbf"), [("LEFT_FID", "N", 9, 0), ("RIGHT_FID", "N", 9, 0)],
+                        {"LEFT_FID": left, "RIGHT_FID": right})
+    shapefile.write_dbf(str(d / "PointsGCS.dbf"), [("inner", "N", 9, 0)], {"inner": np.arange(len(p["store"]))})
+    np.save(tmp_path / "feats.npy", p["store"])
+    io = FeatureIO()
+    io.ReadFeatures(str(tmp_path / "feats.npy"))
+    assert test_for_shp(io, None, str(tmp_path / "tile.shp"), str(d / "lines.shp"), str(d / "PointsGCS.shp")) == 0
+    col = shapefile.DbfTable(str(d / "lines.dbf")).column_float("simi")
+    keep = np.arange(len(left)) != 7
+    assert np.isnan(col[7])
+    np.testing.assert_allclose(col[keep], p["simi"][keep], rtol=1e-3)
