@@ -385,6 +385,8 @@ class MergeEngine:
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.H, self.W, self.R, self.D, self.C, self.N = int(H), int(W), int(n_regions), int(D), int(C), int(n_points)
         self.cap = default_edge_capacity(n_regions, H, W) if edge_capacity is None else int(edge_capacity)
+        self.logits = None
+        self._means_fresh = self._init_fresh = False     # run() prepares both beside the raster pass
         self._alloc()
 
     def _alloc(self):
@@ -528,7 +530,7 @@ class MergeEngine:
             L.check(L.dm_score_l2(_p(self.mean), _p(self.norm2), D, _p(self.keys), _p(n_edges), cap, _p(only),
                                   _p(self.scores), s), "dm_score_l2")
         else:
-            if getattr(self, "logits", None) is None or self.logits.shape != (cap, mlp.n_out):
+            if self.logits is None or self.logits.shape != (cap, mlp.n_out):
                 self.logits = torch.empty((cap, mlp.n_out), dtype=_F32, device=self.dev)
             L.check(L.dm_score_mlp_bf16(_p(self.mean), D, _p(self.keys), _p(n_edges), cap, _p(mlp.blob), mlp.in_features,
                                         mlp.hidden, mlp.n_out, _p(self.logits), None, s), "dm_score_mlp_bf16")
@@ -545,10 +547,10 @@ class MergeEngine:
         n_edges = self.counts[0:1]
         if mlp is not None and mlp.in_features != 2 * D:
             raise ValueError("the pair-MLP takes concat(mean[lo], mean[hi]): in_features must be 2 D")
-        if not getattr(self, "_init_fresh", False):
+        if not self._init_fresh:
             self._merge_init()
         self._init_fresh = False
-        if not getattr(self, "_means_fresh", False):      # run() computes them on the side stream right after the pooling
+        if not self._means_fresh:                         # run() computes them on the side stream right after the pooling
             self._mean_all()
         self._means_fresh = False
         self._score(mlp, None)
