@@ -11,6 +11,8 @@ by the CUDA library; there is no numpy fallback -- a CUDA device is required.
 """
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 import torch
 
@@ -59,7 +61,10 @@ def pool_and_score(store, point_id_fields, left_ids, right_ids):
     simi [E] float64, what the reference writes to the 'simi' OFTReal field :217-219)."""
     dev = _dev()
     off, ids = membership_csr(point_id_fields)
-    store_t = torch.from_numpy(np.ascontiguousarray(store, dtype=np.float32)).to(dev)
+    store = np.ascontiguousarray(store, dtype=np.float32)
+    with warnings.catch_warnings():                      # a read-only memory map is fine: the rows are only copied to the device
+        warnings.simplefilter("ignore", UserWarning)
+        store_t = torch.from_numpy(store).to(dev)
     s, c = pool_points_csr(torch.from_numpy(off).to(dev), torch.from_numpy(ids).to(dev), store_t)
     mean, n2 = region_mean(s, c)
     left = torch.as_tensor(np.asarray(left_ids, np.int64), device=dev)
