@@ -45,8 +45,8 @@ class PolygonConnectPointDataset:
 
     def _open_without_gdal(self):
         """osgeo is not installed: the attribute tables (and point coordinates) are read by the pure-Python
-        adaptor deepmerge_b200.shapefile, which offers the OGR calls this path makes.  The image is only used for
-        its band count here and stays unopened (pass img_dataset= if a GDAL-like raster object is at hand)."""
+        adaptor deepmerge_b200.shapefile, which offers the OGR calls this path makes, and the image (only used
+        for its band count here) by deepmerge_b200.geotiff."""
         from . import shapefile
         for attr, path in (("polygon", self.polygon_path), ("point", self.point_path), ("line", self.polyline_path)):
             ds = shapefile.Open(path, 1) if path else None
@@ -56,6 +56,11 @@ class PolygonConnectPointDataset:
                 continue
             setattr(self, attr + "_dataset", ds)
             setattr(self, attr + "_layer", ds.GetLayer(0))
+        if self.img_dataset is None and self.image_path:
+            from . import geotiff
+            self.img_dataset = geotiff.Open(self.image_path)
+            if self.img_dataset is None:
+                raise ValueError("Can not open {0}".format(self.image_path))
 
     def __len__(self):
         return len(self.data)
@@ -126,9 +131,12 @@ def get_scales(inner_scale, object_scale, cfg_scales=SCALES):
 
 def cut_image(image, window):
     """Zero-padded window of a [C, H, W] uint8 raster, MyUtils2.py:330-360, including the reference's clamp
-    `start + size >= src -> size = src - start` (so a window that ends exactly at the border is cut the same)."""
+    `start + size >= src -> size = src - start` (so a window that ends exactly at the border is cut the same).
+    `image` is a numpy array or a GDAL-like dataset (RasterCount / RasterXSize / RasterYSize / ReadAsArray), as in
+    the reference -- e.g. what deepmerge_b200.geotiff.Open returns."""
     x0, y0, w, h = (int(v) for v in window)
-    C, H, W = image.shape
+    dataset = image if hasattr(image, "ReadAsArray") else None
+    C, H, W = (image.RasterCount, image.RasterYSize, image.RasterXSize) if dataset is not None else image.shape
     out = np.zeros((C, h, w), np.uint8)
     ox = oy = 0
     dw, dh = w, h
@@ -143,8 +151,89 @@ def cut_image(image, window):
     if y0 + dh >= H:
         dh = H - y0
     if dw > 0 and dh > 0:
-        out[:, oy:oy + dh, ox:ox + dw] = image[:, y0:y0 + dh, x0:x0 + dw]
+        out[:, oy:oy + dh, ox:ox + dw] = (dataset.ReadAsArray(x0, y0, dw, dh) if dataset is not None
+                                          else image[:, y0:y0 + dh, x0:x0 + dw])
     return out
+
+
+DESIGNED_FIELDS = ("area", "peri", "len", "width", "smooth", "std0", "std1", "std2", "mean0", "mean1", "mean2",
+                   "shapeness", "compact", "bright", "border")       # get_designed_features, MyUtils2.py:250-284
+
+
+class ExtractFeatureDataset:
+    """The sample-point side of the reference's ExtractFeatureDataset (MyUtils2.py:213-437): one item per feature
+    of PointsGCS.shp -- its 15 designed attributes, the four window scales from `inner` / `object`, and its pixel
+    position in the scene raster.  Files are opened with GDAL/OGR when installed, else with the adaptors
+    deepmerge_b200.shapefile / deepmerge_b200.geotiff.  `windows()` returns everything for all points as arrays (what
+    the batched GPU cutter `cut_windows` takes); `window_patches(i)` is the per-point, per-scale zero-padded cut of
+    get_patches_by_scales BEFORE its INTER_AREA resize (the resize and the network are the missing part of N1)."""
+
+    def __init__(self, image_path, point_path, *, img_dataset=None, point_layer=None):
+        self.image_path, self.point_path = image_path, point_path
+        self.data = []
+        self._windows = None
+        self.img_dataset, self.point_layers, self.point_dataset = img_dataset, point_layer, None
+        self.add_data(image_path, point_path)
+
+    def __len__(self):
+        return len(self.data)
+
+    def add_data(self, img_path, point_path):
+        if self.point_layers is None or self.img_dataset is None:
+            if point_path is None or img_path is None:
+                return None
+            try:
+                from osgeo import gdal, ogr
+                ds = ogr.GetDriverByName("ESRI Shapefile").Open(point_path, 1)
+                img = gdal.Open(img_path, gdal.GA_ReadOnly)
+            except ImportError:
+                from . import geotiff, shapefile
+                ds, img = shapefile.Open(point_path, 1), geotiff.Open(img_path)
+            if ds is None or ds.GetLayer(0) is None:
+                raise ValueError("Can not open {0}".format(point_path))
+            if img is None:
+                raise ValueError("Can not open {0}".format(img_path))
+            self.point_dataset, self.point_layers, self.img_dataset = ds, ds.GetLayer(0), img
+        self.band_num = self.img_dataset.RasterCount
+        self.point_layers.ResetReading()
+        feature = self.point_layers.GetNextFeature()
+        while feature is not None:
+            self.data.append(int(feature.GetFID()))
+            feature = self.point_layers.GetNextFeature()
+        return len(self.data)
+
+    def windows(self):
+        """-> dict of arrays over all points: ids int64 [N], designed float32 [N, 19] (15 attributes + 4 scale
+        factors, as get_all_features concatenates them), scales int64 [N, 4], xpix / ylin int64 [N]."""
+        if self._windows is not None:
+            return self._windows
+        ids = np.asarray(self.data, np.int64)
+        table = getattr(self.point_layers, "table", None)
+        if table is not None and getattr(self.point_layers, "points", None) is not None:       # whole columns at once
+            attr = np.stack([table.column_float(f)[ids] for f in DESIGNED_FIELDS], axis=1)
+            inner, obj = table.column_int("inner")[ids], table.column_int("object")[ids]
+            X, Y = (c[ids] for c in self.point_layers.points)
+        else:
+            feats = [self.point_layers.GetFeature(int(i)) for i in ids]
+            attr = np.asarray([[float(f.GetField(n)) for n in DESIGNED_FIELDS] for f in feats], np.float64).reshape(-1, 15)
+            inner = np.asarray([int(f.GetField("inner")) for f in feats], np.int64)
+            obj = np.asarray([int(f.GetField("object")) for f in feats], np.int64)
+            X = np.asarray([f.GetGeometryRef().GetX() for f in feats], np.float64)
+            Y = np.asarray([f.GetGeometryRef().GetY() for f in feats], np.float64)
+        interval = obj - inner                                           # get_scales, MyUtils2.py:300-327
+        scales = np.stack([inner, obj, obj + interval, obj + 2 * interval], axis=1).astype(np.int64)
+        factors = scales / np.asarray(SCALES, np.float64)
+        xpix, ylin = geo_to_pixel(self.img_dataset.GetGeoTransform(), X, Y)
+        self._windows = {"ids": ids, "designed": np.concatenate([attr, factors], axis=1).astype(np.float32),
+                         "scales": scales, "xpix": xpix, "ylin": ylin}
+        return self._windows
+
+    def window_patches(self, index):
+        """[uint8 [C, s, s] for s in the point's four scales]: cut_image at calculate_left_top_point_and_size."""
+        w = self.windows()
+        k = int(np.nonzero(w["ids"] == self.data[index])[0][0])
+        return [cut_image(self.img_dataset, calculate_left_top_point_and_size(int(w["xpix"][k]), int(w["ylin"][k]), int(s)))
+                for s in w["scales"][k]]
 
 
 def cut_windows(image, xpix, ylin, size):
