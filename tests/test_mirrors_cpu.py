@@ -78,3 +78,33 @@ def test_join_adjacency_form():
         m.neighbours_from_join("1,2", 5)            # self missing: list.remove raises like the reference
     off, ids = m.membership_from_points(["4,9", "", "7"])
     assert off.tolist() == [0, 2, 2, 3] and ids.tolist() == [4, 9, 7]
+
+
+def test_checkpoint_dictionary_round_trip(tmp_path):
+    """Train_SMT.py:318-340 / :164-198: keys, file-name pattern, resume of network + optimizer state."""
+    import time
+    import torch
+    from deepmerge_b200 import checkpoint
+    from deepmerge_b200.Nets import MLP
+    torch.manual_seed(0)
+    net = MLP(dims=(200, 250, 2))
+    net.name, net.depth, net.input_image_scales = "pairMLP", 3, [32, 64, 128, 1]
+    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9)
+    net.fc1.weight.grad = torch.ones_like(net.fc1.weight)
+    opt.step()
+    t = time.struct_time((2024, 3, 9, 14, 5, 0, 0, 0, 0))
+    assert checkpoint.model_name(99, t) == "model-2024-3-9_14-5_100epochs.pth"
+    p = checkpoint.save(str(tmp_path / checkpoint.model_name(4, t)), net, opt, 4, 123.456)
+    raw = torch.load(p, weights_only=False)
+    assert tuple(raw.keys()) == checkpoint.KEYS and raw["time"] == 123.46 and raw["epoch"] == 4
+    assert raw["name"] == "pairMLP" and raw["depth"] == 3 and raw["scales"] == [32, 64, 128, 1]
+    net2 = MLP(dims=(200, 250, 2))
+    opt2 = torch.optim.SGD(net2.parameters(), lr=0.1, momentum=0.9)
+    ck = checkpoint.load(p, net2, opt2)
+    assert ck["epoch"] == 4 and all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), net2.state_dict().values()))
+    assert torch.equal(opt2.state_dict()["state"][0]["momentum_buffer"], opt.state_dict()["state"][0]["momentum_buffer"])
+    # a bare state_dict (the reference's `weights` argument) loads too
+    torch.save(net.state_dict(), str(tmp_path / "weights.pth"))
+    net3 = MLP(dims=(200, 250, 2))
+    assert checkpoint.load(str(tmp_path / "weights.pth"), net3)["epoch"] == -1
+    assert torch.equal(net3.fc3.bias, net.fc3.bias)
