@@ -120,14 +120,13 @@ class FeatureIO:
             self.h5py_file = None
 
 
-def score_layers(store, polygon_layer, line_layer, scorer=None):
+def score_layers(store, polygon_layer, line_layer):
     """test_for_shp's loop (ExtractFeatures.py:164-222) for EVERY line of `line_layer` (the reference `break`s
     after the first): pool each polygon's `PointID` rows of `store`, score every LEFT_FID / RIGHT_FID pair with
     the Euclidean distance and write it to the line attribute `simi` (created as OFTReal when missing).
     Layers are OGR layers or deepmerge_b200.shapefile.ShapefileLayer objects.  -> (fids, left, right, simi).
-    `scorer(store, point_id_fields, left, right) -> (means, simi)` defaults to the GPU path `pool_and_score`."""
+    Pooling and scoring run on the GPU (`pool_and_score`); only the attribute tables are host work."""
     from . import shapefile
-    scorer = pool_and_score if scorer is None else scorer
     fids, left, right = [], [], []
     if isinstance(line_layer, shapefile.ShapefileLayer):            # whole columns at once
         t = line_layer.table
@@ -151,7 +150,7 @@ def score_layers(store, polygon_layer, line_layer, scorer=None):
         for i in range(polygon_layer.GetFeatureCount()):
             v = polygon_layer.GetFeature(i).GetField("PointID")
             point_ids.append("" if v is None else str(v))
-    _, simi = scorer(np.asarray(store), point_ids, left, right)
+    _, simi = pool_and_score(np.asarray(store), point_ids, left, right)
     if line_layer.GetLayerDefn().GetFieldIndex("simi") < 0:
         try:
             from osgeo import ogr

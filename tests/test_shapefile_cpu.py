@@ -178,7 +178,11 @@ class OgrOnly:
 
 
 @pytest.mark.parametrize("generic", [False, True])
-def test_score_layers_writes_simi_for_every_kept_line(golden_dir, tmp_path, generic):
+def test_score_layers_writes_simi_for_every_kept_line(golden_dir, tmp_path, generic, monkeypatch):
+    # the file handling is what is under test here: the GPU scorer is replaced by a host stand-in (the real one
+    # runs in tests/test_gpu_mirrors.py::test_test_for_shp_on_real_shapefiles)
+    import deepmerge_b200.ExtractFeatures as E
+    monkeypatch.setattr(E, "pool_and_score", cpu_scorer)
     p = np.load(os.path.join(golden_dir, "pool_score.npz"))
     fields, left, right = list(p["fields"]), p["left"].copy(), p["right"].copy()
     left[3] = -1                                                                      # a line on the tile border: skipped
@@ -187,8 +191,7 @@ def test_score_layers_writes_simi_for_every_kept_line(golden_dir, tmp_path, gene
                         {"LEFT_FID": left, "RIGHT_FID": right})
     poly = shapefile.ShapefileLayer(str(tmp_path / "poly.shp"))
     lines = shapefile.ShapefileLayer(str(tmp_path / "lines.shp"), 1)
-    fids, l, r, simi = score_layers(p["store"], OgrOnly(poly) if generic else poly, OgrOnly(lines) if generic else lines,
-                                    scorer=cpu_scorer)
+    fids, l, r, simi = score_layers(p["store"], OgrOnly(poly) if generic else poly, OgrOnly(lines) if generic else lines)
     keep = np.arange(len(left)) != 3
     assert fids.tolist() == np.nonzero(keep)[0].tolist() and np.array_equal(l, left[keep]) and np.array_equal(r, right[keep])
     np.testing.assert_allclose(simi, p["simi"][keep], rtol=1e-3)                      # the executed reference's scores
