@@ -55,6 +55,17 @@ def membership_csr(point_id_fields, sep=" "):
     return offsets, np.asarray(ids, np.int32)
 
 
+def region_of_point(point_id_fields, n_points, sep=" "):
+    """'PointID' strings of polygons 0..R-1 -> int32 [n_points]: the polygon every sample point belongs to (-1 for a
+    point no polygon lists) -- the membership form `merge_scene(region_of_point=...)` takes."""
+    off, ids = membership_csr(point_id_fields, sep)
+    rop = np.full(int(n_points), -1, np.int32)
+    if ids.size and (ids.min() < 0 or ids.max() >= n_points):
+        raise ValueError("PointID refers to a point outside the feature store")
+    rop[ids] = np.repeat(np.arange(len(point_id_fields), dtype=np.int32), np.diff(off))
+    return rop
+
+
 def pool_and_score(store, point_id_fields, left_ids, right_ids):
     """Mean-pool every polygon's member rows of the feature store (np.mean(axis=0) semantics, bit
     exact) and score every (left, right) edge with the Euclidean distance -> (means [R,D] float32,

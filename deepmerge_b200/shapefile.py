@@ -505,3 +505,126 @@ def Open(path, update=0):
         return ShapefileDataSource(path, update)
     except ValueError:
         return None
+
+
+# ---------------------------------------------------------------------------------------------
+# polygon geometry -> label raster (the step from the reference's vector artefacts to the raster-native path)
+# ---------------------------------------------------------------------------------------------
+_POLY_TYPES = (5, 15, 25)           # Polygon, PolygonZ, PolygonM
+
+
+def read_polygons(path):
+    """-> list (one entry per record, FID order) of lists of rings, each ring a float64 [k, 2] array of (X, Y);
+    null shapes give an empty list.  Outer rings and holes are not distinguished: filling uses the even-odd rule."""
+    raw, st = _shp_header(path)
+    if st not in _POLY_TYPES:
+        raise ValueError("{0} is not a polygon shapefile (shape type {1})".format(path, st))
+    out = []
+    off, end = 100, len(raw)
+    while off + 8 <= end:
+        (clen,) = struct.unpack_from(">i", raw, off + 4)
+        body = off + 8
+        rings = []
+        if body + 44 <= end and struct.unpack_from("<i", raw, body)[0] in _POLY_TYPES:
+            n_parts, n_points = struct.unpack_from("<ii", raw, body + 36)
+            parts = list(struct.unpack_from("<%di" % n_parts, raw, body + 44)) + [n_points]
+            pts = np.frombuffer(raw, "<f8", 2 * n_points, body + 44 + 4 * n_parts).reshape(n_points, 2)
+            rings = [pts[parts[i]:parts[i + 1]].copy() for i in range(n_parts)]
+        out.append(rings)
+        off = body + 2 * clen
+    return out
+
+
+def write_polygon_shp(path, polygons):
+    """Polygon .shp + .shx; `polygons` = list of lists of rings ([k, 2] arrays, closed or not)."""
+    def closed(r):
+        r = np.asarray(r, np.float64).reshape(-1, 2)
+        return r if len(r) and np.array_equal(r[0], r[-1]) else np.concatenate([r, r[:1]])
+
+    polys = [[closed(r) for r in rings] for rings in polygons]
+    allpts = np.concatenate([r for rings in polys for r in rings]) if any(polys) else np.zeros((1, 2))
+    bbox = (allpts[:, 0].min(), allpts[:, 1].min(), allpts[:, 0].max(), allpts[:, 1].max())
+
+    def header(file_words):
+        h = bytearray(100)
+        struct.pack_into(">i", h, 0, 9994)
+        struct.pack_into(">i", h, 24, file_words)
+        struct.pack_into("<ii", h, 28, 1000, 5)
+        struct.pack_into("<dddd", h, 36, *bbox)
+        return bytes(h)
+
+    recs, idx = bytearray(), bytearray()
+    for i, rings in enumerate(polys):
+        if rings:
+            pts = np.concatenate(rings)
+            starts = np.cumsum([0] + [len(r) for r in rings[:-1]])
+            content = struct.pack("<i4dii", 5, pts[:, 0].min(), pts[:, 1].min(), pts[:, 0].max(), pts[:, 1].max(),
+                                  len(rings), len(pts))
+            content += struct.pack("<%di" % len(rings), *starts.tolist()) + np.ascontiguousarray(pts, "<f8").tobytes()
+        else:
+            content = struct.pack("<i", 0)
+        idx += struct.pack(">ii", (100 + len(recs)) // 2, len(content) // 2)
+        recs += struct.pack(">ii", i + 1, len(content) // 2) + content
+    base = path[:-4] if path.lower().endswith(".shp") else path
+    with open(base + ".shp", "wb") as f:
+        f.write(header((100 + len(recs)) // 2) + bytes(recs))
+    with open(base + ".shx", "wb") as f:
+        f.write(header((100 + len(idx)) // 2) + bytes(idx))
+
+
+def rasterize_polygons(polygons, geotransform, height, width, nodata=-1, ids=None):
+    """int32 [height, width] label raster: a pixel takes the id (default: the polygon's FID) of the polygon that
+    contains its CENTRE (even-odd rule over all rings of the polygon, so holes stay empty; the later polygon wins
+    where two overlap; pixels in no polygon keep `nodata`, which the RAG kernels treat like the reference's -1 ids).
+    North-up rasters only (geotransform[2] == geotransform[4] == 0)."""
+    gt = [float(v) for v in geotransform]
+    if gt[2] != 0.0 or gt[4] != 0.0 or gt[1] == 0.0 or gt[5] == 0.0:
+        raise ValueError("rasterize_polygons needs a north-up geotransform")
+    out = np.full((int(height), int(width)), nodata, np.int32)
+    for fid, rings in enumerate(polygons):
+        if not rings:
+            continue
+        label = fid if ids is None else int(ids[fid])
+        # pixel-space coordinates in which pixel (r, c) has its centre at (c + 0.5, r + 0.5)
+        segs = []
+        for r in rings:
+            r = np.asarray(r, np.float64).reshape(-1, 2)
+            if len(r) < 3:
+                continue
+            px = (r[:, 0] - gt[0]) / gt[1]
+            py = (r[:, 1] - gt[3]) / gt[5]
+            if px[0] != px[-1] or py[0] != py[-1]:
+                px, py = np.append(px, px[0]), np.append(py, py[0])
+            segs.append(np.stack([px[:-1], py[:-1], px[1:], py[1:]], axis=1))
+        if not segs:
+            continue
+        s = np.concatenate(segs)
+        r0 = max(0, int(np.ceil(min(s[:, 1].min(), s[:, 3].min()) - 0.5)))
+        r1 = min(int(height) - 1, int(np.floor(max(s[:, 1].max(), s[:, 3].max()) - 0.5)))
+        if r1 < r0:
+            continue
+        yc = np.arange(r0, r1 + 1, dtype=np.float64) + 0.5                     # [rows]
+        x0, y0, x1, y1 = s[:, 0:1], s[:, 1:2], s[:, 2:3], s[:, 3:4]            # [segments, 1]
+        crosses = (y0 <= yc) != (y1 <= yc)                                     # half-open rule: no double count at vertices
+        with np.errstate(divide="ignore", invalid="ignore"):
+            xi = x0 + (yc - y0) * (x1 - x0) / (y1 - y0)
+        xi = np.where(crosses, xi, np.inf)
+        xi.sort(axis=0)                                                        # crossings of every row, ascending
+        n_pairs = int(crosses.sum(axis=0).max()) // 2
+        if n_pairs == 0:
+            continue
+        xa, xb = xi[0:2 * n_pairs:2], xi[1:2 * n_pairs:2]                      # [pairs, rows]: fill [xa, xb)
+        ok = np.isfinite(xa) & np.isfinite(xb)
+        ca = np.clip(np.ceil(np.where(ok, xa, 0.0) - 0.5), 0, width).astype(np.int64)    # first column with centre >= xa
+        cb = np.clip(np.ceil(np.where(ok, xb, 0.0) - 0.5), 0, width).astype(np.int64)    # first column with centre >= xb
+        ok &= cb > ca
+        if not ok.any():
+            continue
+        c_lo, c_hi = int(ca[ok].min()), int(cb[ok].max())
+        rows = np.broadcast_to(np.arange(yc.shape[0]), ok.shape)[ok]
+        d = np.zeros((yc.shape[0], c_hi - c_lo + 1), np.int32)                 # +1 / -1 marks, then a running sum per row
+        np.add.at(d, (rows, ca[ok] - c_lo), 1)
+        np.add.at(d, (rows, cb[ok] - c_lo), -1)
+        inside = np.cumsum(d, axis=1)[:, :-1] > 0
+        out[r0:r1 + 1, c_lo:c_hi][inside] = label
+    return out

@@ -210,3 +210,108 @@ def test_feature_store_npy(tmp_path):
     with pytest.raises(IndexError):
         io.GetFeaturesByID(17)
     io.Close()
+
+
+def rect_partition(H, W, rng, min_side=3):
+    """Random partition of an H x W raster into axis-aligned rectangles -> (labels, [(r0, r1, c0, c1), ...])."""
+    rects, todo = [], [(0, H, 0, W)]
+    while todo:
+        r0, r1, c0, c1 = todo.pop()
+        h, w = r1 - r0, c1 - c0
+        if (h < 2 * min_side and w < 2 * min_side) or rng.random() < 0.15:
+            rects.append((r0, r1, c0, c1))
+        elif w >= h and w >= 2 * min_side:
+            m = int(rng.integers(c0 + min_side, c1 - min_side + 1))
+            todo += [(r0, r1, c0, m), (r0, r1, m, c1)]
+        elif h >= 2 * min_side:
+            m = int(rng.integers(r0 + min_side, r1 - min_side + 1))
+            todo += [(r0, m, c0, c1), (m, r1, c0, c1)]
+        else:
+            rects.append((r0, r1, c0, c1))
+    labels = np.zeros((H, W), np.int32)
+    for i, (r0, r1, c0, c1) in enumerate(rects):
+        labels[r0:r1, c0:c1] = i
+    return labels, rects
+
+
+def test_polygon_shapefile_to_label_raster(tmp_path):
+    """Polygons on disk -> the int32 label raster the raster-native path starts from (label = FID)."""
+    rng = np.random.default_rng(5)
+    H, W = 90, 130
+    gt = (4000.0, 2.0, 0.0, 7000.0, 0.0, -2.0)
+    labels, rects = rect_partition(H, W, rng)
+    polys = [[np.array([[gt[0] + c0 * gt[1], gt[3] + r0 * gt[5]], [gt[0] + c1 * gt[1], gt[3] + r0 * gt[5]],
+                        [gt[0] + c1 * gt[1], gt[3] + r1 * gt[5]], [gt[0] + c0 * gt[1], gt[3] + r1 * gt[5]]])]
+             for r0, r1, c0, c1 in rects]
+    shapefile.write_polygon_shp(str(tmp_path / "tile.shp"), polys)
+    shapefile.write_dbf(str(tmp_path / "tile.dbf"), [("PointID", "C", 20, 0)], {"PointID": ["%d" % i for i in range(len(polys))]})
+    back = shapefile.read_polygons(str(tmp_path / "tile.shp"))
+    assert len(back) == len(polys) and all(np.array_equal(b[0][:4], p[0]) for b, p in zip(back, polys))
+    got = shapefile.rasterize_polygons(back, gt, H, W)
+    assert got.dtype == np.int32 and np.array_equal(got, labels)          # pixel-aligned cells come back exactly
+    # a window of the same scene (shifted origin), ids from an attribute instead of the FID
+    sub = shapefile.rasterize_polygons(back, (gt[0] + 10 * gt[1], gt[1], 0.0, gt[3] + 20 * gt[5], 0.0, gt[5]), 30, 40,
+                                       ids=np.arange(len(polys)) + 1000)
+    assert np.array_equal(sub, labels[20:50, 10:50] + 1000)
+    with pytest.raises(ValueError):
+        shapefile.rasterize_polygons(back, (0, 1, 0.1, 0, 0, -1), 4, 4)
+    with pytest.raises(ValueError, match="not a polygon"):
+        shapefile.read_polygons(_point_file(tmp_path))
+
+
+def _point_file(tmp_path):
+    shapefile.write_point_shp(str(tmp_path / "pts.shp"), [1.0], [2.0])
+    return str(tmp_path / "pts.shp")
+
+
+def test_rasterize_holes_overlaps_and_brute_force(tmp_path):
+    # a ring inside a ring is a hole (even-odd); the later polygon wins where two overlap; uncovered pixels stay nodata
+    sq = lambda a, b: np.array([[a, a], [b, a], [b, b], [a, b]], float)
+    gt = (0.0, 1.0, 0.0, 12.0, 0.0, -1.0)
+    lab = shapefile.rasterize_polygons([[sq(1, 11), sq(4, 8)], [sq(5, 7)], []], gt, 12, 12)
+    want = np.full((12, 12), -1, np.int32)
+    want[1:11, 1:11] = 0
+    want[4:8, 4:8] = -1
+    want[5:7, 5:7] = 1
+    assert np.array_equal(lab, want)
+    # random (non-convex) polygons against a per-pixel even-odd test
+    rng = np.random.default_rng(1)
+    H, W = 50, 70
+    polys = []
+    for _ in range(25):
+        cx, cy = rng.uniform(0, W), rng.uniform(0, H)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, int(rng.integers(3, 10))))
+        rad = rng.uniform(1, 12, len(ang))
+        polys.append([np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], 1)])
+    got = shapefile.rasterize_polygons(polys, (0.0, 1.0, 0.0, 0.0, 0.0, 1.0), H, W)
+    cc, rr = np.meshgrid(np.arange(W) + 0.5, np.arange(H) + 0.5)
+    want = np.full((H, W), -1, np.int32)
+    for fid, (ring,) in enumerate(polys):
+        inside = np.zeros((H, W), bool)
+        for (a, b), (c, d) in zip(ring, np.roll(ring, -1, axis=0)):
+            cross = (b <= rr) != (d <= rr)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                xi = a + (rr - b) * (c - a) / (d - b)
+            inside ^= cross & (cc >= xi)
+        want[inside] = fid
+    assert np.array_equal(got, want)
+    # PolygonZ records (type 15) carry the same header; round trip through the writer's type-5 layout patched to 15
+    shapefile.write_polygon_shp(str(tmp_path / "z.shp"), polys[:3])
+    raw = bytearray((tmp_path / "z.shp").read_bytes())
+    struct.pack_into("<i", raw, 32, 15)
+    off = 100
+    while off < len(raw):
+        (clen,) = struct.unpack_from(">i", raw, off + 4)
+        struct.pack_into("<i", raw, off + 8, 15)
+        off += 8 + 2 * clen
+    (tmp_path / "z.shp").write_bytes(bytes(raw))
+    z = shapefile.read_polygons(str(tmp_path / "z.shp"))
+    assert all(np.allclose(a[0][:-1], b[0]) for a, b in zip(z, polys[:3]))
+
+
+def test_region_of_point_from_point_id_fields():
+    from deepmerge_b200.ExtractFeatures import region_of_point
+    rop = region_of_point(["3 1", "", "0 4"], 6)
+    assert rop.dtype == np.int32 and rop.tolist() == [2, 0, -1, 0, 2, -1]
+    with pytest.raises(ValueError):
+        region_of_point(["7"], 3)
