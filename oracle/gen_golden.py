@@ -204,6 +204,23 @@ def golden_geometry(ref, rng):
              cfg_scales=np.array(ref.config.configs.scales), geo=geo, px=px, **cuts)
 
 
+def golden_resize(ref, rng):
+    """ExtractFeatureDataset.resize_data :362-376 (cv2.resize INTER_AREA per band, then / 255) on the patch sizes the
+    loader meets: integer shrink factors 1, 2, 3, 4, fractional shrinks, enlargements, the 1 x 1 environment patch."""
+    ds = object.__new__(ref.MyUtils2.ExtractFeatureDataset)
+    cases = [(32, 32), (64, 32), (96, 32), (128, 32), (50, 32), (45, 32), (20, 32), (31, 32), (128, 64), (90, 64),
+             (70, 64), (40, 64), (200, 128), (129, 128), (100, 128), (64, 128), (37, 1), (64, 1), (150, 1)]
+    out = {}
+    for i, (s_, t) in enumerate(cases):
+        ds.band_num = 3 if i == 4 else 1                                       # (small fixtures: one band mostly)
+        patch = rng.integers(0, 256, size=(ds.band_num, s_, s_)).astype(np.uint8)
+        if i % 3 == 0:
+            patch[:, : s_ // 3] = 0                                            # zero padding of a border window
+        out[f"in{i}"] = patch
+        out[f"out{i}"] = ds.resize_data(patch, t, t)
+    np.savez_compressed(os.path.join(OUT, "resize.npz"), cases=np.array(cases), **out)
+
+
 def main():
     if not ref_shim.available():
         raise SystemExit("needs /root/reference (build container only)")
@@ -211,7 +228,7 @@ def main():
     ref = ref_shim.load()
     rng = np.random.default_rng(20261018)
     for fn in (golden_euclid, golden_pool_score, golden_mlp, golden_loss, golden_edge_reader,
-               golden_pair_sampler, golden_geometry):
+               golden_pair_sampler, golden_geometry, golden_resize):
         fn(ref, rng)
         print("wrote", fn.__name__)
 

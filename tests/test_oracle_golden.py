@@ -204,3 +204,27 @@ def test_synth_scene_is_bimodal():
     scored = (cnt[lo] > 0) & (cnt[hi] > 0)       # edge cells whose seed lies outside the image have no points
     assert scored.mean() > 0.9
     assert np.all(s[same & scored] < 0.35) and np.all(s[~same & scored] > 5.0)
+
+
+def test_patch_resize_matches_the_executed_reference(golden_dir):
+    """oracle.resize_area restates cv2's INTER_AREA (the arithmetic behind ExtractFeatureDataset.resize_data,
+    MyUtils2.py:362-376); the golden outputs were produced by executing the reference's resize_data.  Bit exact."""
+    from oracle.resize_area import resize_data
+    g_ = g(golden_dir, "resize.npz")
+    for i, (s, t) in enumerate(g_["cases"]):
+        got = resize_data(g_[f"in{i}"], int(t))
+        want = g_[f"out{i}"]
+        assert got.dtype == np.float32 and got.shape == want.shape, (s, t)
+        assert np.array_equal(got, want), (s, t, int((got != want).sum()))
+
+
+def test_patch_resize_against_opencv_when_installed():
+    """Wider sweep against cv2 itself (the reference's unpinned dependency; 4.13 in the build container)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle.resize_area import resize_area_u8
+    rng = np.random.default_rng(9)
+    for t in (32, 64, 128, 1):
+        for s in sorted(set(rng.integers(2, 3 * max(t, 40), 14).tolist() + [t, 2 * t, 3 * t, 4 * t, 5 * t])):
+            a = rng.integers(0, 256, (s, s), dtype=np.uint8)
+            want = cv2.resize(a, (t, t), interpolation=cv2.INTER_AREA).reshape(t, t)
+            assert np.array_equal(resize_area_u8(a, t), want), (s, t)
