@@ -255,3 +255,91 @@ def cut_windows(image, xpix, ylin, size):
     with torch.cuda.device(image.device):
         L.check(L.dm_cut_windows(_p(image), C, H, W, _p(x0), _p(y0), len(xpix), size, _p(out), _stream()), "dm_cut_windows")
     return out
+
+
+def area_tables(s, t):
+    """Coefficient tables of cv2.resize(.., (t, t), INTER_AREA) for a square source of side s (the layout
+    dm_resize_area takes): -> (mode, ti int32 or None, tf float32 or None).  OpenCV's published rules: an integer
+    factor needs no table (mode 0); a fractional shrink weighs every source cell by its overlap with the
+    destination cell, float32 weights (mode 1); an enlargement is its "area-mode" bilinear with 11-bit
+    fixed-point coefficients (mode 2)."""
+    import math
+    s, t = int(s), int(t)
+    if s % t == 0:
+        return 0, None, None
+    f32 = np.float32
+    if s > t:
+        scale = s / t
+        start, src, w = [0], [], []
+        for d in range(t):
+            lo = d * scale
+            hi = lo + scale
+            cell = min(scale, s - lo)
+            i1 = math.ceil(lo)
+            i2 = min(math.floor(hi), s - 1)
+            i1 = min(i1, i2)
+            if i1 - lo > 1e-3:
+                src.append(i1 - 1)
+                w.append(f32((i1 - lo) / cell))
+            for i in range(i1, i2):
+                src.append(i)
+                w.append(f32(1.0 / cell))
+            if hi - i2 > 1e-3:
+                src.append(i2)
+                w.append(f32(min(min(hi - i2, 1.0), cell) / cell))
+            start.append(len(src))
+        return 1, np.asarray(start + src, np.int32), np.asarray(w, np.float32)
+    inv = t / s
+    scale = 1.0 / inv
+    sx, a0, a1, xmax = [], [], [], t
+    for d in range(t):
+        i = math.floor(d * scale)
+        fx = f32((d + 1) - (i + 1) * inv)
+        fx = f32(0) if fx <= 0 else f32(fx - math.floor(fx))
+        if i + 1 >= s:
+            xmax = min(xmax, d)
+            if i >= s - 1:
+                fx, i = f32(0), s - 1
+        sx.append(i)
+        a0.append(int(np.rint((f32(1) - fx) * f32(2048))))
+        a1.append(int(np.rint(fx * f32(2048))))
+    return 2, np.asarray(sx + a0 + a1 + [xmax], np.int32), None
+
+
+def resize_windows(windows, t):
+    """resize_data (MyUtils2.py:362-376) for a batch on the GPU: uint8 CUDA tensor [n, C, s, s] (e.g. from
+    cut_windows) -> float32 [n, C, t, t] in [0, 1], bit-identical to cv2.resize(INTER_AREA) / 255 per band."""
+    import torch
+    from ._lib import lib
+    from .raster import _p, _stream
+    if not windows.is_cuda or windows.dtype != torch.uint8 or windows.dim() != 4 or windows.shape[2] != windows.shape[3]:
+        raise ValueError("windows must be a uint8 CUDA tensor [n, C, s, s]")
+    windows = windows.contiguous()
+    n, C, s, _ = windows.shape
+    mode, ti, tf = area_tables(s, t)
+    ti_d = torch.from_numpy(ti).to(windows.device) if ti is not None else None
+    tf_d = torch.from_numpy(tf).to(windows.device) if tf is not None else None
+    out = torch.empty((n, C, int(t), int(t)), dtype=torch.float32, device=windows.device)
+    L = lib()
+    with torch.cuda.device(windows.device):
+        L.check(L.dm_resize_area(_p(windows), n * C, s, int(t), mode, _p(ti_d), _p(tf_d), _p(out), _stream()), "dm_resize_area")
+    return out
+
+
+def point_patches(image, windows, cfg_scales=SCALES):
+    """get_patches_by_scales (MyUtils2.py:286-298) for ALL points on the GPU: `image` uint8 CUDA tensor [C, H, W],
+    `windows` = ExtractFeatureDataset.windows() -> list of 4 float32 tensors [N, C, cfg, cfg] (cfg = 32, 64, 128, 1).
+    Points are grouped by their window size, each group is cut (cut_windows) and resized (resize_windows) at once."""
+    import torch
+    n = len(windows["ids"])
+    xpix, ylin = np.asarray(windows["xpix"], np.int64), np.asarray(windows["ylin"], np.int64)
+    out = []
+    for k, cfg in enumerate(cfg_scales):
+        sizes = np.asarray(windows["scales"])[:, k]
+        patches = torch.empty((n, image.shape[0], cfg, cfg), dtype=torch.float32, device=image.device)
+        for s in np.unique(sizes):
+            sel = np.nonzero(sizes == s)[0]
+            cut = cut_windows(image, xpix[sel], ylin[sel], int(s))
+            patches[torch.as_tensor(sel, device=image.device)] = resize_windows(cut, cfg)
+        out.append(patches)
+    return out

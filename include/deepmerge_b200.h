@@ -176,6 +176,17 @@ int dm_pool_boundary(const int32_t* labels, int64_t rows_own, int64_t rows_avail
 int dm_cut_windows(const uint8_t* image, int64_t C, int64_t H, int64_t W, const int32_t* x0, const int32_t* y0,
                    int64_t n, int64_t size, uint8_t* out, dm_stream_t stream);
 
+/* "Next" row N1, second piece: ExtractFeatureDataset.resize_data (MyUtils2.py:362-376) for a batch of square
+ * uint8 planes [n_planes, s, s] (windows x bands of dm_cut_windows): cv2.resize(.., (t, t), INTER_AREA) bit for
+ * bit, then float32 / 255 -> out float32 [n_planes, t, t].
+ *   mode 0: s % t == 0 (integer shrink or copy), no tables.
+ *   mode 1: fractional shrink; ti = start[t + 1] ++ src[E] (int32), tf = weight[E] (float32): entries
+ *           start[d] .. start[d + 1] - 1 of destination index d, the same table for both axes.
+ *   mode 2: enlargement; ti = sx[t] ++ a0[t] ++ a1[t] ++ xmax (int32), tf unused.
+ * The tables depend on (s, t) only; deepmerge_b200.MyUtils2.area_tables builds them. */
+int dm_resize_area(const uint8_t* patches, int64_t n_planes, int64_t s, int64_t t, int mode, const int32_t* ti,
+                   const float* tf, float* out, dm_stream_t stream);
+
 /* ----------------------------------------------------------------------------------- *
  * R6  Edge score = Euclidean distance between pooled means, the reference's expanded
  *     formula sqrt(max(0,|x|^2+|y|^2-2x.y)) in fp32 (ExtractFeatures.py:119-147, called

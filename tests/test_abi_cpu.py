@@ -55,6 +55,9 @@ def test_bad_arguments_are_rejected_without_cuda(L):
     assert L.dm_pool_points_csr(None, None, None, 3, 5, 100, None, None, None) == bad   # ld < D
     assert L.dm_rag_scan(None, 4, 6, 4, 4, None, 0, 0, 4, 1, 1, None, None, None, None, 10, None, None, 0, None) == bad
     assert L.dm_contrastive_fwd_bwd(None, None, None, 0, 100, 1.0, None, None, None, None) == bad
+    assert L.dm_resize_area(None, 4, 50, 32, 0, None, None, None, None) == bad        # mode 0 needs an integer factor
+    assert L.dm_resize_area(None, 4, 50, 32, 1, None, None, None, None) == bad        # tables / buffers missing
+    assert L.dm_resize_area(None, 0, 64, 32, 0, None, None, None, None) == 0          # nothing to do
     with pytest.raises(ValueError):
         L.check(bad, "x")
     with pytest.raises(RuntimeError):

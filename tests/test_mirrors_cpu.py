@@ -108,3 +108,22 @@ def test_checkpoint_dictionary_round_trip(tmp_path):
     net3 = MLP(dims=(200, 250, 2))
     assert checkpoint.load(str(tmp_path / "weights.pth"), net3)["epoch"] == -1
     assert torch.equal(net3.fc3.bias, net.fc3.bias)
+
+
+def test_area_tables_agree_with_the_oracle_restatement():
+    """The product's host-side table builder (what dm_resize_area consumes) and the oracle's independent restatement
+    of OpenCV's INTER_AREA rules give the same tables for every (source, target) size the loader can meet."""
+    from oracle import resize_area as ora
+    for t in (32, 64, 128, 1):
+        for s in range(1, 3 * max(t, 40)):
+            mode, ti, tf = MyUtils2.area_tables(s, t)
+            if s % t == 0:
+                assert mode == 0 and ti is None and tf is None
+            elif s > t:
+                di, si, al = ora._area_table(s, t)
+                start = np.searchsorted(np.asarray(di), np.arange(t + 1))
+                assert mode == 1 and np.array_equal(ti[:t + 1], start) and np.array_equal(ti[t + 1:], si)
+                assert tf.dtype == np.float32 and np.array_equal(tf, np.asarray(al, np.float32))
+            else:
+                sx, a0, a1, xmax = ora._linear_table(s, t)
+                assert mode == 2 and np.array_equal(ti, np.concatenate([sx, a0, a1, [xmax]]))
