@@ -11,15 +11,10 @@
 // The tables depend only on (s, t) and are built on the host (deepmerge_b200/MyUtils2.py: area_tables).
 // One CTA per plane (window x band); HBM traffic is the patch bytes in and 4 t^2 bytes out.
 #include "common.cuh"
+#include "resize_core.cuh"
 
 namespace dm {
 namespace resize {
-
-__device__ __forceinline__ float to_unit(int v) {
-    v = v < 0 ? 0 : (v > 255 ? 255 : v);
-    return __fdiv_rn((float)v, 255.0f);
-}
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // ti (mode 1): start[0..t] then src[0..E);  tf: weight[0..E)
 // ti (mode 2): sx[0..t), a0[0..t), a1[0..t), xmax
@@ -30,54 +25,15 @@ __global__ void __launch_bounds__(256) resize_area_kernel(const uint8_t* __restr
     const uint8_t* P = patches + (size_t)blockIdx.x * s * s;
     float* O = out + (size_t)blockIdx.x * t * t;
     if (mode == 0) {
-        const int k = s / t;
-        const float inv = 1.0f / (float)(k * k);
-        for (int o = threadIdx.x; o < t * t; o += blockDim.x) {
-            const int dy = o / t, dx = o - dy * t;
-            int sum = 0;
-            for (int v = 0; v < k; ++v)
-                for (int u = 0; u < k; ++u) sum += P[(dy * k + v) * s + dx * k + u];
-            const int r = k == 1 ? sum : (k == 2 ? (sum + 2) >> 2 : __float2int_rn(__fmul_rn((float)sum, inv)));
-            O[o] = to_unit(r);
-        }
+        for (int o = threadIdx.x; o < t * t; o += blockDim.x) O[o] = shrink_integer(P, s, t, o / t, o % t);
     } else if (mode == 1) {
         const int32_t* start = ti;
         const int32_t* src = ti + t + 1;
-        for (int o = threadIdx.x; o < s * t; o += blockDim.x) {
-            const int sy = o / t, dx = o - sy * t;
-            float acc = 0.0f;
-            for (int e = start[dx]; e < start[dx + 1]; ++e)
-                acc = __fadd_rn(acc, __fmul_rn((float)P[sy * s + clampi(src[e], 0, s - 1)], tf[e]));
-            buf[o] = acc;
-        }
+        for (int o = threadIdx.x; o < s * t; o += blockDim.x) buf[o] = shrink_row(P, s, t, o / t, o % t, start, src, tf);
         __syncthreads();
-        for (int o = threadIdx.x; o < t * t; o += blockDim.x) {
-            const int dy = o / t, dx = o - dy * t;
-            const int e0 = start[dy], e1 = start[dy + 1];
-            float acc = 0.0f;
-            if (e0 < e1) acc = __fmul_rn(tf[e0], buf[clampi(src[e0], 0, s - 1) * t + dx]);
-            for (int e = e0 + 1; e < e1; ++e)
-                acc = __fadd_rn(acc, __fmul_rn(tf[e], buf[clampi(src[e], 0, s - 1) * t + dx]));
-            O[o] = to_unit(__float2int_rn(acc));
-        }
+        for (int o = threadIdx.x; o < t * t; o += blockDim.x) O[o] = shrink_col(buf, s, t, o / t, o % t, start, src, tf);
     } else {
-        const int32_t *sx = ti, *a0 = ti + t, *a1 = ti + 2 * t;
-        const int xmax = ti[3 * t];
-        for (int o = threadIdx.x; o < t * t; o += blockDim.x) {
-            const int dy = o / t, dx = o - dy * t;
-            const int x0 = clampi(sx[dx], 0, s - 1), x1 = min(x0 + 1, s - 1);
-            const int y0 = clampi(sx[dy], 0, s - 1), y1 = min(y0 + 1, s - 1);
-            int S0, S1;
-            if (dx >= xmax) {
-                S0 = (int)P[y0 * s + x0] * 2048;
-                S1 = (int)P[y1 * s + x0] * 2048;
-            } else {
-                S0 = (int)P[y0 * s + x0] * a0[dx] + (int)P[y0 * s + x1] * a1[dx];
-                S1 = (int)P[y1 * s + x0] * a0[dx] + (int)P[y1 * s + x1] * a1[dx];
-            }
-            const int r = (((a0[dy] * (S0 >> 4)) >> 16) + ((a1[dy] * (S1 >> 4)) >> 16) + 2) >> 2;
-            O[o] = to_unit(r);
-        }
+        for (int o = threadIdx.x; o < t * t; o += blockDim.x) O[o] = enlarge(P, s, t, o / t, o % t, ti);
     }
 }
 
