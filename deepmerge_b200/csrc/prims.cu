@@ -545,7 +545,9 @@ int sort_pairs(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t cap
         A.n_dev = n_dev; A.n_max = cap;
         A.hist = w.hist; A.totals = w.totals; A.bar = w.bar;
         A.id_bits = id_bits; A.passes = passes; A.tiles_cap = (int)w.tiles;
-        return launch_fused(A, cap, s);
+        if (launch_fused(A, cap, s) == DM_OK) return DM_OK;
+        (void)cudaGetLastError();       // the cooperative launch was refused (e.g. no room for a co-resident grid
+                                        // under a profiler or a partitioned GPU): take the one-launch-per-phase path
     }
     const unsigned tiles = w.tiles;
     uint64_t *ka = keys, *kb = w.k2;
@@ -598,6 +600,8 @@ __global__ void unique_scatter(const uint64_t* __restrict__ keys, const uint32_t
         atomicAdd(&out_lens[run], lens_in[src]);
     }
 }
+
+__global__ void clamp_count(const int64_t* n_dev, int64_t cap, int64_t* out) { *out = *n_dev < cap ? *n_dev : cap; }
 
 __global__ void copy_runs(const uint64_t* __restrict__ k, const uint32_t* __restrict__ l, const float* __restrict__ sc,
                           const int64_t* __restrict__ n_dev, uint64_t* __restrict__ ko, uint32_t* __restrict__ lo,
@@ -660,11 +664,16 @@ int sort_unique(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t ca
         A.out_keys = out_keys; A.out_lens = out_lens; A.out_scores = out_scores; A.n_out = n_out_dev;
         A.tile_heads = (uint32_t*)unique_ws;               // unique_ws_bytes(cap) >= tiles words
         A.back_keys = back_keys; A.back_lens = back_lens; A.back_scores = back_scores; A.back_n = back_n;
-        return launch_fused(A, cap, s);
+        if (launch_fused(A, cap, s) == DM_OK) return DM_OK;
+        (void)cudaGetLastError();       // the cooperative launch was refused (e.g. no room for a co-resident grid
+                                        // under a profiler or a partitioned GPU): take the one-launch-per-phase path
     }
-    DM_TRY(sort_pairs(keys, vals, n_dev, cap, id_bits, key_bits, sort_ws, s, false));
+    // one launch per phase: n = min(*n_dev, cap) like the fused kernel (a raw list may have overflowed its capacity)
+    int64_t* n_clamped = (int64_t*)(carve_sort_ws(sort_ws, cap).bar + 2);
+    DM_COUNT_LAUNCH(); clamp_count<<<1, 1, 0, s>>>(n_dev, cap, n_clamped);
+    DM_TRY(sort_pairs(keys, vals, n_clamped, cap, id_bits, key_bits, sort_ws, s, false));
     DM_TRY(unique_reduce(keys, gather_lens ? vals : nullptr, gather_lens ? gather_lens : vals,
-                         gather_lens ? gather_scores : nullptr, n_dev, cap, sentinel, out_keys, out_lens, out_scores,
+                         gather_lens ? gather_scores : nullptr, n_clamped, cap, sentinel, out_keys, out_lens, out_scores,
                          n_out_dev, unique_ws, s));
     if (back_keys) {
         const unsigned g = (unsigned)imax64(1, imin64(ceil_div(cap, 256), (int64_t)num_sms() * 8));
