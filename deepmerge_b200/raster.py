@@ -58,6 +58,23 @@ class RAG:
     def endpoints(self):
         return self.edge_keys >> 32, self.edge_keys & 0xFFFFFFFF
 
+    def attributes(self):
+        """The designed polygon attributes of the reference's tables (MyUtils1.py:79-114) that follow from this
+        pass alone (first part): `area` (pixels), `peri` (pixel sides facing another label, nodata
+        or the image border), per band `mean<c>` and `std<c>` (population deviation) and `bright` (mean of the band
+        means) -> dict of float32 tensors [R] ([R, C] for mean / std), NaN for regions without pixels.  The
+        bounding-box attributes (len, width, smooth, shapeness, compact, border) are not produced yet."""
+        area = self.area.to(torch.float64)
+        out = {"area": area.to(_F32), "peri": self.perimeter.to(_F32)}
+        if self.band_sum is not None:
+            n = torch.where(area > 0, area, torch.full_like(area, float("nan")))[:, None]
+            mean = self.band_sum.to(torch.float64) / n
+            var = self.band_sumsq.to(torch.float64) / n - mean * mean
+            out["mean"] = mean.to(_F32)
+            out["std"] = torch.sqrt(torch.clamp(var, min=0.0)).to(_F32)
+            out["bright"] = mean.mean(dim=1).to(_F32)
+        return out
+
 
 def default_edge_capacity(n_regions, H, W):
     return int(max(1 << 16, min(2 * H * W, 8 * n_regions + 4 * (H + W))))

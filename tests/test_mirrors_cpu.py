@@ -127,3 +127,28 @@ def test_area_tables_agree_with_the_oracle_restatement():
             else:
                 sx, a0, a1, xmax = ora._linear_table(s, t)
                 assert mode == 2 and np.array_equal(ti, np.concatenate([sx, a0, a1, [xmax]]))
+
+
+def test_rag_attributes_from_the_pooled_statistics():
+    """RAG.attributes(): area / peri / mean / std / bright of every region from the integer sums of the raster pass
+    (device-agnostic tensor arithmetic; the sums themselves are checked bit-exactly by the GPU parity tests)."""
+    import torch
+    from deepmerge_b200.raster import RAG
+    from oracle import oracle_np as o
+    sc = o.synth_scene(96, 128, 40, C=3)
+    R = sc["n_regions"]
+    s, q = o.pool_bands(sc["labels"], sc["image"], R)
+    keys, blen, area, perim = o.build_rag(sc["labels"], R)[:4]
+    rag = RAG(torch.from_numpy(keys.view(np.int64)), torch.from_numpy(blen.view(np.int32)), torch.from_numpy(area),
+              torch.from_numpy(perim), torch.zeros(R, dtype=torch.int64), torch.from_numpy(s.view(np.int64)),
+              torch.from_numpy(q.view(np.int64)))
+    a = rag.attributes()
+    for r in range(R):
+        px = sc["image"][sc["labels"] == r].astype(np.float64)
+        assert a["area"][r].item() == len(px) and a["peri"][r].item() == perim[r]
+        if len(px):
+            np.testing.assert_allclose(a["mean"][r].numpy(), px.mean(axis=0), rtol=1e-6)
+            np.testing.assert_allclose(a["std"][r].numpy(), px.std(axis=0), rtol=1e-5, atol=1e-4)
+            np.testing.assert_allclose(a["bright"][r].item(), px.mean(axis=0).mean(), rtol=1e-6)
+        else:
+            assert torch.isnan(a["mean"][r]).all()
