@@ -152,3 +152,34 @@ def test_rag_attributes_from_the_pooled_statistics():
             np.testing.assert_allclose(a["bright"][r].item(), px.mean(axis=0).mean(), rtol=1e-6)
         else:
             assert torch.isnan(a["mean"][r]).all()
+
+
+def test_point_patches_grouping_logic(monkeypatch):
+    """point_patches groups the points by window size and scatters every group's patches back in point order.  The
+    two GPU calls are replaced by host stand-ins here (cut_image per point, the oracle resize), so that the grouping
+    itself is checked without a device; the real kernels are covered by tests/test_zz_gpu_resize.py."""
+    import torch
+    from oracle.resize_area import resize_data
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, (2, 90, 110), dtype=np.uint8)
+
+    def fake_cut(image, xpix, ylin, size):
+        a = image.numpy()
+        return torch.from_numpy(np.stack([MyUtils2.cut_image(a, MyUtils2.calculate_left_top_point_and_size(int(x), int(y), size))
+                                          for x, y in zip(xpix, ylin)]))
+
+    def fake_resize(windows, t):
+        return torch.from_numpy(np.stack([resize_data(w, t) for w in windows.numpy()]))
+
+    monkeypatch.setattr(MyUtils2, "cut_windows", fake_cut)
+    monkeypatch.setattr(MyUtils2, "resize_windows", fake_resize)
+    n = 10
+    inner, obj = rng.integers(6, 12, n), rng.integers(14, 20, n)          # few distinct sizes -> real groups
+    scales = np.stack([inner, obj, 2 * obj - inner, 3 * obj - 2 * inner], axis=1)
+    w = {"ids": np.arange(n), "scales": scales, "xpix": rng.integers(1, 111, n), "ylin": rng.integers(1, 91, n)}
+    got = MyUtils2.point_patches(torch.from_numpy(img), w)
+    for k, cfg in enumerate(MyUtils2.SCALES):
+        assert tuple(got[k].shape) == (n, 2, cfg, cfg)
+        for i in range(n):
+            win = MyUtils2.calculate_left_top_point_and_size(int(w["xpix"][i]), int(w["ylin"][i]), int(scales[i, k]))
+            assert np.array_equal(got[k][i].numpy(), resize_data(MyUtils2.cut_image(img, win), cfg)), (i, k)
