@@ -174,7 +174,6 @@ def test_rag_nodata_and_every_pixel_its_own_region(cuda):
 
 def test_rag_capacity_overflow_is_reported_and_retried(cuda):
     L = np.arange(64 * 256, dtype=np.int32).reshape(64, 256)
-    rag, raw = check_rag(cuda, L, 64 * 256, capacity=1000, return_raw=True) if False else (None, None)
     from deepmerge_b200 import build_rag
     rag = build_rag(T(L, cuda), 64 * 256, capacity=1000)          # too small on purpose
     keys, blen, area, per = o.build_rag(L, 64 * 256)
@@ -205,6 +204,20 @@ def test_rag_forced_fallback_equals_tma(cuda, monkeypatch):
     sc = o.synth_scene(130, 512, 400, C=4)
     monkeypatch.setenv("DM_RAG_NO_TMA", "1")
     check_rag(cuda, sc["labels"], sc["n_regions"], sc["image"])
+
+
+@pytest.mark.parametrize("env", [{"DM_RAG_CFG": "1"}, {"DM_RAG_CFG": "2"}, {"DM_RAG_CFG": "3"}, {"DM_RAG_CFG": "4"},
+                                 {"DM_RAG_KERNEL": "v1"}])
+def test_rag_alternative_kernel_shapes(cuda, monkeypatch, env):
+    """The measurement-only shapes of the raster kernel (and the round-1 kernel) give the same answer."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sc = o.synth_scene(300, 1024, 350, C=4)
+    check_rag(cuda, sc["labels"], sc["n_regions"], sc["image"])
+    rng = np.random.default_rng(3)
+    L = rng.integers(0, 50, size=(70, 300)).astype(np.int32)
+    L[rng.random(L.shape) < 0.1] = -1
+    check_rag(cuda, L, 50, rng.integers(0, 256, size=(70, 300, 4)).astype(np.uint8))
 
 
 def test_rag_row_tiles_sum_to_whole(cuda):
