@@ -937,6 +937,7 @@ static bool allow_tma_env() {
 int run(const Params& P, int C, cudaStream_t s) {
     const bool tma = allow_tma_env();
     const char* e = getenv("DM_RAG_KERNEL");            // "v1": the label-cache kernel of round 1 (A/B measurements)
+    if (e && e[0] == 's') return run_split(P, C, tma, s);    // "split": the warp-specialised kernel
     if (!(e && e[0] == 'v' && e[1] == '1')) return run_blocks(P, C, tma, s);
     switch (C) {
         case 0: return launch<Cfg<0, 8, 2, 16>>(P, tma, s);

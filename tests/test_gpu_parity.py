@@ -207,7 +207,8 @@ def test_rag_forced_fallback_equals_tma(cuda, monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"DM_RAG_CFG": "1"}, {"DM_RAG_CFG": "2"}, {"DM_RAG_CFG": "3"}, {"DM_RAG_CFG": "4"},
-                                 {"DM_RAG_KERNEL": "v1"}])
+                                 {"DM_RAG_KERNEL": "v1"}, {"DM_RAG_KERNEL": "split"}, {"DM_RAG_KERNEL": "split", "DM_RAG_CFG": "1"},
+                                 {"DM_RAG_KERNEL": "split", "DM_RAG_CFG": "2"}, {"DM_RAG_KERNEL": "split", "DM_RAG_CFG": "3"}])
 def test_rag_alternative_kernel_shapes(cuda, monkeypatch, env):
     """The measurement-only shapes of the raster kernel (and the round-1 kernel) give the same answer."""
     for k, v in env.items():
@@ -218,6 +219,8 @@ def test_rag_alternative_kernel_shapes(cuda, monkeypatch, env):
     L = rng.integers(0, 50, size=(70, 300)).astype(np.int32)
     L[rng.random(L.shape) < 0.1] = -1
     check_rag(cuda, L, 50, rng.integers(0, 256, size=(70, 300, 4)).astype(np.uint8))
+    sc = o.synth_scene(3000, 2048, 24000, C=4)        # long strips: the item buffers / the ring wrap around many times
+    check_rag(cuda, sc["labels"], sc["n_regions"], sc["image"])
 
 
 def test_rag_row_tiles_sum_to_whole(cuda):

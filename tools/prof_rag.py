@@ -19,10 +19,11 @@ eng = MergeEngine(side, side, sc.n_regions, 100, C=C, n_points=sc.feats.shape[0]
 variants = [v for v in os.environ.get("DM_PROF_VARIANTS", "").split(",") if v]
 for var in variants or [""]:
   if var:
-    k, _, v = var.partition("=")
     for kk in ("DM_RAG_CFG", "DM_RAG_KERNEL"):
         os.environ.pop(kk, None)
-    os.environ[k] = v
+    for kv in var.split("+"):
+        k, _, v = kv.partition("=")
+        os.environ[k] = v
   ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
   for a, b in ev:
       eng.stats.zero_()
