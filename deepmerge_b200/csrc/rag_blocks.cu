@@ -390,10 +390,6 @@ int run_blocks(const Params& P, int C, bool allow_tma, cudaStream_t s) {
                 case 1: return launch<Cfg<4, 4, 2, 10, 64>>(P, allow_tma, s);
                 case 2: return launch<Cfg<4, 4, 3, 9, 48>>(P, allow_tma, s);
                 case 3: return launch<Cfg<4, 8, 2, 8, 48>>(P, allow_tma, s);
-                case 4: return launch<Cfg<4, 4, 2, 13, 40>>(P, allow_tma, s);
-                case 5: return launch<Cfg<4, 4, 2, 8, 48>>(P, allow_tma, s);
-                case 6: return launch<Cfg<4, 4, 2, 10, 48>>(P, allow_tma, s);
-                case 7: return launch<Cfg<4, 4, 2, 4, 48>>(P, allow_tma, s);
                 default: return launch<Cfg<4, 4, 2, 12, 48>>(P, allow_tma, s);
             }
         }

@@ -84,7 +84,6 @@ bool make_map_2d(CUtensorMap* m, const void* base, uint64_t dim0, uint64_t dim1,
                  uint32_t box1);
 void set_last_path(int path);
 int run_blocks(const Params& P, int C, bool allow_tma, cudaStream_t s);   // rag_blocks.cu
-int run_split(const Params& P, int C, bool allow_tma, cudaStream_t s);    // rag_split.cu
 
 }  // namespace rag
 }  // namespace dm

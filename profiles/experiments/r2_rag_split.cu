@@ -1,24 +1,22 @@
-// R1 raster pass, warp-specialised: SCAN warps and ITEM warps of one persistent CTA per SM.
+// R1 raster pass, warp-specialised: pairs of a SCAN warp and an ITEM warp in one persistent CTA per SM.
 //
 // Same arithmetic as rag_blocks.cu (rag_core.cuh: 4 x 4 blocks, fast path for one-label windows, process_item for the
 // rest); what changes is who runs it.  In the mixed kernel every warp alternates between the scan loop and item passes:
 // 166 registers and 19 KB of shared memory per warp allow 12 warps per SM, and the kernel is bound by per-warp stalls
 // (fixed-latency dependencies, branch resolution) at 3 warps per scheduler: 46 % of the issue slots.  Here
-//   * NSW scan warps walk the strips: TMA-fed private stage ring, window test,
-//     unmasked statistics into the lane's accumulators, a private region table for label changes.  A block that is not
-//     a one-label window is written, as a self-contained item, straight into a CTA-wide RING of item batches;
-//   * NIW item warps own the hash tables and do nothing but take full batches of 32
-//     items out of the ring, one item per lane (process_item), so every pass runs 32 wide whatever a single strip
-//     produces.
+//   * the scan warp of a pair walks the strips: TMA-fed private stage ring, window test, unmasked statistics into the
+//     lane's accumulators, a private region table for label changes.  A block that is not a one-label window is
+//     written, as a self-contained item, straight into the pair's RING of item batches;
+//   * the item warp of the pair owns the hash tables of the strip and does nothing but take full batches of 32 items
+//     out of the ring, one item per lane (process_item).  (A CTA-wide ring feeding any item warp was measured first:
+//     it loses the strip locality of the tables -- 2.7 x the raw edge entries, 0.76 ms.)
+// Neither role needs more than ~95 registers once nothing is called out of line, so 18 warps fit where 12 did.
 // The ring is NB batches of 32 slots; batch b has a FULL mbarrier (32 arrivals: one per item written, release) and a
 // CONSUMED generation counter (stored, release, by the item warp after its pass; a scan lane about to write generation
-// t of a batch waits until t generations have been consumed -- a counter, not an mbarrier parity: with one slow item
-// warp the other batches keep cycling and a writer can be two generations ahead of a batch, which a parity wait would
-// let through).  Slots are reserved with one shared-memory atomicAdd per
-// producing warp and block row; batches are consumed round robin (item warp c takes batches c, c + NIW, ...), so
-// there is no consumer-side counter.  End of input: the last scan warp to finish publishes the item total, completes
-// the last (partial) batch's barrier with the missing arrival count and raises `finished`; an item warp whose next
-// batch lies beyond the total leaves.
+// t of a batch waits until t generations have been consumed).  The scan warp numbers its items itself (one producer per
+// ring: no atomics).  End of input: the scan warp publishes its item total, completes the last (partial) batch's
+// barrier with the missing arrival count and raises `finished`; the item warp leaves when its next batch lies beyond
+// the total.
 #include "rag_tables.cuh"
 
 namespace dm {
@@ -27,12 +25,13 @@ namespace split {
 
 using namespace blk;
 
-template <int C_, int NSW_, int NIW_, int NB_>
+template <int C_, int NP_, int NB_>
 struct Cfg {
-    static constexpr int C = C_, NSW = NSW_, NIW = NIW_, NB = NB_;
+    static constexpr int C = C_, NP = NP_, NB = NB_;          // bands, warp pairs per CTA, batches per ring
+    static constexpr int NSW = NP;
     static constexpr int TH = 4, NS = 2;
     static constexpr int CW = C_ > 0 ? C_ : 1;
-    static constexpr int NWARPS = NSW + NIW;
+    static constexpr int NWARPS = 2 * NP;
     static constexpr int THREADS = NWARPS * 32;
     static constexpr int LAB_BOX = align128(TH * LAB_PITCH * 4);
     static constexpr int IMG_ROW_WORDS = STRIP_W * C / 4;
@@ -44,19 +43,16 @@ struct Cfg {
     static constexpr int RING_BYTES = SLOTS * ITEM_VECS * 16;
     static constexpr int TABLE_WORDS = RS * (3 + 2 * C) + ES * 3 + 4;
     static constexpr int TABLE_BYTES = align128(TABLE_WORDS * 4 + NS * 8);     // + the stage barriers of a scan warp
-    static constexpr int SCAN_BYTES = NS * STAGE_BYTES + TABLE_BYTES;
-    static constexpr int CTRL_BYTES = align128(NB * 16 + 16);                   // full[NB], consumed[NB] (padded), 4 control words
-    static constexpr int SMEM_BYTES = 128 + CTRL_BYTES + RING_BYTES + NSW * SCAN_BYTES + NIW * TABLE_BYTES;
+    static constexpr int CTRL_BYTES = 128;                                      // full[NB], consumed[NB], total, finished
+    static constexpr int PAIR_BYTES = NS * STAGE_BYTES + 2 * TABLE_BYTES + RING_BYTES + CTRL_BYTES;
+    static constexpr int SMEM_BYTES = 128 + NP * PAIR_BYTES;
     static constexpr int FLUSH_UNITS = FLUSH_ROWS / TH;
-    // an mbarrier wait tells phases apart by parity only, so a waiter must never be two phases ahead of its barrier:
-    static_assert(NB % NIW == 0, "every batch slot is always consumed by the same item warp, in order");
+    static_assert(NB * 12 + 8 <= CTRL_BYTES, "control block");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 struct Ctrl {
-    unsigned reserve;       // item slots reserved so far
-    unsigned done;          // scan warps that have finished
-    unsigned final_total;   // number of items, once known (~0u before)
+    unsigned final_total;   // number of items of the pair, once known (~0u before)
     unsigned finished;      // final_total is valid and the last batch has been completed
 };
 
@@ -121,37 +117,40 @@ rag_split_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
-    uint64_t* full_b = (uint64_t*)smem;                       // [NB]
-    unsigned* consumed = (unsigned*)(full_b + NB);            // [NB] generations consumed of every batch
-    Ctrl* ctrl = (Ctrl*)(full_b + 2 * NB);
-    uint4* ring = (uint4*)(smem + CF::CTRL_BYTES);
-    unsigned char* scan_base = smem + CF::CTRL_BYTES + CF::RING_BYTES;
-    unsigned char* item_base = scan_base + CF::NSW * CF::SCAN_BYTES;
+    // Roles by scheduler: warps w with (w & 3) < 2 scan, the others process items, so that each of the four schedulers (and
+    // its small L0 instruction cache) runs one role's code only (NP even); otherwise the first NP warps scan.
+    constexpr bool BY_SMSP = (CF::NP % 2 == 0);
+    const bool scan_role = BY_SMSP ? ((warp & 3) < 2) : (warp < CF::NP);
+    const int pair = BY_SMSP ? ((warp >> 2) * 2 + (warp & 1)) : (warp < CF::NP ? warp : warp - CF::NP);
+    unsigned char* pbase = smem + (size_t)pair * CF::PAIR_BYTES;       // this pair's arena
+    unsigned char* wbase = pbase;                                      // stages | scan table | item table | ring | control
+    uint4* ring = (uint4*)(pbase + NS * CF::STAGE_BYTES + 2 * CF::TABLE_BYTES);
+    uint64_t* full_b = (uint64_t*)(pbase + NS * CF::STAGE_BYTES + 2 * CF::TABLE_BYTES + CF::RING_BYTES);   // [NB]
+    unsigned* consumed = (unsigned*)(full_b + NB);                     // [NB] generations consumed of every batch
+    Ctrl* ctrl = (Ctrl*)(consumed + NB);
 
-    if (threadIdx.x == 0) {
+    if (scan_role && lane == 0) {
         for (int b = 0; b < NB; ++b) {
             mbar_init(&full_b[b], 32);
             consumed[b] = 0;
         }
-        ctrl->reserve = 0;
-        ctrl->done = 0;
         ctrl->final_total = ~0u;
         ctrl->finished = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp < CF::NSW) {
+    if (scan_role) {
         // =============================================================================================================
         // SCAN role
         // =============================================================================================================
-        unsigned char* wbase = scan_base + (size_t)warp * CF::SCAN_BYTES;
         unsigned* tab = (unsigned*)(wbase + NS * CF::STAGE_BYTES);
         const Tab<C> T = Tab<C>::from(tab);
         uint64_t* stage_bar = (uint64_t*)(tab + ((CF::TABLE_WORDS + 1) & ~1));
+        unsigned produced = 0;                                             // items written to the ring so far (warp-uniform)
 
         const long long total_units = (long long)P.tiles_x * P.tiles_y;
-        const long long gw = (long long)blockIdx.x * CF::NSW + warp;
+        const long long gw = (long long)blockIdx.x * CF::NSW + pair;
         const long long u_begin = min(total_units, gw * (long long)P.tiles_per_cta);
         const long long u_end = min(total_units, u_begin + P.tiles_per_cta);
         const int my_units = (int)(u_end - u_begin);
@@ -299,11 +298,8 @@ rag_split_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant
             }
             const unsigned bal = __ballot_sync(0xffffffffu, is_item);
             if (bal) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&ctrl->reserve, (unsigned)__popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
                 if (is_item) {
-                    const unsigned idx = base + __popc(bal & lanemask_lt());
+                    const unsigned idx = produced + __popc(bal & lanemask_lt());
                     const unsigned bq = idx >> 5;                       // batch number
                     const unsigned g = bq % NB, gen = bq / NB;
                     wait_consumed(&consumed[g], gen, P.counters);      // the batch's previous generations are consumed
@@ -328,6 +324,7 @@ rag_split_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant
                     it[(6 + C) * SLOTS] = make_uint4((unsigned)x0, (unsigned)y0, 0u, 0u);
                     mbar_arrive_release(&full_b[g], 1u);
                 }
+                produced += __popc(bal);
             }
             up = a3;
             contiguous = (j + 1 < P.tiles_y);
@@ -349,27 +346,21 @@ rag_split_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant
             if (forced_flush || T.used[0] > RS / 2) drain_tables_impl<C>(tab, &P, lane);
         }
 
-        // ---- end of this warp's input -------------------------------------------------------------------------------
+        // ---- end of this warp's input: every item has been written ---------------------------------------------------
         __syncwarp();
         if (lane == 0) {
+            ctrl->final_total = produced;
             __threadfence_block();
-            const unsigned prev = atomicAdd(&ctrl->done, 1u);
-            if (prev == (unsigned)CF::NSW - 1u) {                 // the last scan warp: every item has been written
-                const unsigned total = ld_volatile_u32(&ctrl->reserve);
-                ctrl->final_total = total;
-                __threadfence_block();
-                const unsigned rem = total & 31u;
-                if (rem) mbar_arrive_release(&full_b[(total >> 5) % NB], 32u - rem);
-                __threadfence_block();
-                atomicExch(&ctrl->finished, 1u);
-            }
+            const unsigned rem = produced & 31u;
+            if (rem) mbar_arrive_release(&full_b[(produced >> 5) % NB], 32u - rem);
+            __threadfence_block();
+            atomicExch(&ctrl->finished, 1u);
         }
     } else {
         // =============================================================================================================
         // ITEM role
         // =============================================================================================================
-        const int c = warp - CF::NSW;
-        unsigned* tab = (unsigned*)(item_base + (size_t)c * CF::TABLE_BYTES);
+        unsigned* tab = (unsigned*)(pbase + NS * CF::STAGE_BYTES + CF::TABLE_BYTES);
         const Tab<C> T = Tab<C>::from(tab);
         T.rkey[lane] = EMPTY_LABEL;
         T.rarea[lane] = 0;
@@ -389,7 +380,7 @@ rag_split_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constant
         const InlineSink<C> sink{T, P};
         int batches_since_drain = 0;
 
-        for (unsigned bq = (unsigned)c;; bq += (unsigned)CF::NIW) {
+        for (unsigned bq = 0;; ++bq) {
             const unsigned gb = bq % NB, parity = (bq / NB) & 1u;
             bool live = true;
             while (!mbar_try_wait(&full_b[gb], parity)) {
@@ -478,19 +469,17 @@ static int launch(const Params& Pin, bool allow_tma, cudaStream_t s) {
 
 }  // namespace split
 
-// <bands, scan warps, item warps, ring batches>.  Neither role needs more than 96 registers once nothing is called
-// out of line, so no setmaxnreg register hand-over between the roles is needed for 20 warps per SM.
+// <bands, warp pairs per CTA, batches per ring>
 int run_split(const Params& P, int C, bool allow_tma, cudaStream_t s) {
     using namespace split;
     if (C != 4) return run_blocks(P, C, allow_tma, s);
     const char* e = getenv("DM_RAG_CFG");
     const int v = e ? atoi(e) : 0;
     switch (v) {
-        case 1: return launch<Cfg<4, 8, 8, 8>>(P, allow_tma, s);
-        case 2: return launch<Cfg<4, 12, 12, 12>>(P, allow_tma, s);
-        case 3: return launch<Cfg<4, 12, 6, 12>>(P, allow_tma, s);
-        case 4: return launch<Cfg<4, 12, 4, 12>>(P, allow_tma, s);
-        default: return launch<Cfg<4, 10, 10, 10>>(P, allow_tma, s);
+        case 1: return launch<Cfg<4, 8, 2>>(P, allow_tma, s);
+        case 2: return launch<Cfg<4, 7, 3>>(P, allow_tma, s);
+        case 3: return launch<Cfg<4, 6, 4>>(P, allow_tma, s);
+        default: return launch<Cfg<4, 9, 2>>(P, allow_tma, s);
     }
 }
 

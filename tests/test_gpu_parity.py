@@ -206,11 +206,9 @@ def test_rag_forced_fallback_equals_tma(cuda, monkeypatch):
     check_rag(cuda, sc["labels"], sc["n_regions"], sc["image"])
 
 
-@pytest.mark.parametrize("env", [{"DM_RAG_CFG": "1"}, {"DM_RAG_CFG": "2"}, {"DM_RAG_CFG": "3"}, {"DM_RAG_CFG": "4"},
-                                 {"DM_RAG_KERNEL": "v1"}, {"DM_RAG_KERNEL": "split"}, {"DM_RAG_KERNEL": "split", "DM_RAG_CFG": "1"},
-                                 {"DM_RAG_KERNEL": "split", "DM_RAG_CFG": "2"}, {"DM_RAG_KERNEL": "split", "DM_RAG_CFG": "3"}])
+@pytest.mark.parametrize("env", [{}, {"DM_RAG_CFG": "1"}, {"DM_RAG_CFG": "2"}, {"DM_RAG_CFG": "3"}])
 def test_rag_alternative_kernel_shapes(cuda, monkeypatch, env):
-    """The measurement-only shapes of the raster kernel (and the round-1 kernel) give the same answer."""
+    """The measurement-only shapes of the raster kernel give the same answer; long strips wrap the item buffers."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     sc = o.synth_scene(300, 1024, 350, C=4)
