@@ -371,6 +371,8 @@ def main():
     ap.add_argument("--cpu-side", type=int, default=3000,
                     help="side of the bounded CPU sample scenes (one per host core; ~1.4 s of numpy work each per step)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="N > 1: skip the (untimed) check of the sharded answer against the single-GPU engine on rank 0")
     ap.add_argument("--config2", action="store_true",
                     help="N > 1 only: run BASELINE.json configs[2] (ONE 40k x 40k scene, ~1M segments, split over the ranks) "
                          "instead of the weak-scaling stack of configs[1] tiles")

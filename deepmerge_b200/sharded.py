@@ -342,6 +342,20 @@ SHARDED_CFG = dict(H=40000, W=40000, R=1000000, C=4, P=4, D=100, tau=0.5, seed=1
 SHARDED_WORKLOAD = "configs[2]: 40k x 40k scene, ~1M segments, row-tile sharded across N B200 with NCCL boundary exchange"
 
 
+def position_checksum(t, first=0, chunk=1 << 24):
+    """64-bit position-weighted checksum of an integer tensor (wraps mod 2^64): sum over i of (t[i] + 2) * w(first + i),
+    w a fixed odd-multiplier hash of the global position -- so that equal checksums of a tile and of the same rows of a
+    whole map mean equal contents in equal places.  Device tensor in, Python int out."""
+    flat = t.reshape(-1)
+    acc = torch.zeros((), dtype=torch.int64, device=t.device)
+    for a in range(0, flat.numel(), chunk):
+        v = flat[a:a + chunk].to(torch.int64)
+        idx = torch.arange(first + a, first + a + v.numel(), dtype=torch.int64, device=t.device)
+        w = ((idx * 0x9E3779B1 + 0x7F4A7C15) & 0xFFFFFFFF) | 1
+        acc += ((v + 2) * w).sum()
+    return int(acc.item())
+
+
 def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks):
     """Weak scaling: every rank owns a tile of H_1 x W_1 / ... -- the N-GPU scene is the single-GPU
     workload's height times N (same tile per GPU), so per-GPU work is fixed as N grows."""
@@ -451,6 +465,34 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
     torch.cuda.synchronize()
     rag_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(rk0[1:], rk1[1:])]))
     res = step()
+    # ---- parity of the multi-process answer (outside every timed region): position-weighted checksums of every
+    # rank's label tile and root table against ONE GPU running the single-GPU engine over the whole scene
+    mine_cs = torch.tensor([position_checksum(res.labels, y0 * W), position_checksum(res.root), res.rounds, res.merges],
+                           dtype=torch.int64, device=dev)
+    all_cs = [torch.zeros_like(mine_cs) for _ in range(world)]
+    dist.all_gather(all_cs, mine_cs)
+    parity_ok, parity_note = None, "skipped (--no-parity)"
+    if rank == 0 and not getattr(args, "no_parity", False):
+        from .raster import MergeEngine
+        try:
+            whole = synth_scene(H, W, R_target, C=C, P=P, D=D, seed=cfg["seed"], device=dev)
+            eng1 = MergeEngine(H, W, R, D, C=C, n_points=whole.feats.shape[0], device=dev)
+            one = eng1.run(whole.labels, whole.feats, cfg["tau"], image=whole.image, xs=whole.xs, ys=whole.ys)
+            root_cs = position_checksum(one.root)
+            bad = []
+            for r in range(world):
+                a, b = tile_bounds(H, world, r)
+                want = [position_checksum(one.labels[a:b], a * W), root_cs, one.rounds, one.merges]
+                if [int(x) for x in all_cs[r].tolist()] != want:
+                    bad.append(r)
+            parity_ok = not bad
+            parity_note = ("label tiles, root table, rounds and merges of all %d ranks equal the single-GPU engine's on the "
+                           "whole %dx%d scene (64-bit position-weighted checksums)" % (world, H, W)) if parity_ok else \
+                          "MISMATCH on ranks %s" % bad
+            del whole, eng1, one
+            torch.cuda.empty_cache()
+        except torch.OutOfMemoryError:
+            parity_note = "skipped: the whole scene does not fit one GPU beside this rank's tile"
     if rank == 0:
         peak, kind = measured_peaks()
         alg = (4 + C) * rows_t * W + 12 * (3 * R // world) + 16 * (R // world) * C
@@ -470,6 +512,7 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
                                       "edge list gathered on every rank",
                        "l2_policy": "inputs larger than L2, no flush needed"},
             "merged_edges_per_s": res.merges / (ms * 1e-3), "segments_after": n_roots, "rounds": res.rounds,
+            "parity_ok": parity_ok, "parity": parity_note,
             "ms_per_step_gathered": ms_gathered,
             "e2e": {"value": H * W / float(tmax[0]) / 1e3, "unit": "Mpx/s", "ms_per_step": float(tmax[0]),
                     "h2d_bytes_per_step": int(t[1]), "d2h_bytes_per_step": int(t[2]),

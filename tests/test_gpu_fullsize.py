@@ -1,7 +1,10 @@
-"""GPU: BASELINE.json configs[1] at FULL size (10k x 10k, 4 bands, ~100k segments) through size-independent
-properties -- the oracle cannot run this size in seconds, so the checks are identities the domain offers:
-pixel-count and checksum conservation, the perimeter / boundary-length identity, row-tile additivity, relabel
-idempotence, run-to-run determinism, and agreement of the merged statistics with a recount of the final map."""
+"""GPU: BASELINE.json configs[1] at FULL size (10k x 10k, 4 bands, ~100k segments).
+
+test_whole_step_against_the_oracle_at_full_size checks the whole step -- RAG, band sums, pooled embeddings, scores,
+merge loop, final label map -- bit for bit against the oracle (the plain-C restatement for the raster stages, which
+takes a few seconds at this size, the numpy restatement for the graph stages).  The other tests are size-independent
+identities the domain offers: pixel-count and checksum conservation, the perimeter / boundary-length identity,
+row-tile additivity, relabel idempotence, run-to-run determinism."""
 import numpy as np
 import pytest
 
@@ -74,7 +77,7 @@ def test_merge_is_deterministic_idempotent_and_consistent(cuda, scene):
     assert bool((root_a <= ids).all())                                           # root = minimum id of the component
     assert int(roots.sum()) == R - a.merges                                      # every merge removes one region
     assert torch.equal(relabel(labels_a, root_a), labels_a)                      # idempotent
-    # the merged statistics equal a recount of the final label map
+    # the merged statistics equal those of the final label map rebuilt from scratch
     again = build_rag(labels_a, R, scene.image)
     assert torch.equal(again.area[roots], area_a[roots]) and int(again.area[~roots].sum()) == 0
     assert torch.equal(again.perimeter[roots], perim_a[roots])
@@ -82,3 +85,46 @@ def test_merge_is_deterministic_idempotent_and_consistent(cuda, scene):
     assert torch.equal(again.edge_keys, a.edge_keys) and torch.equal(again.boundary_len, a.boundary_len[:E])
     # no surviving edge is below the threshold (the loop ran to its fixed point)
     assert a.rounds < 64 and bool((a.scores >= 0.5).all())
+
+
+def test_whole_step_against_the_oracle_at_full_size(cuda, scene):
+    """The BASELINE configuration itself, not a scaled-down stand-in: every integer output of the step equals the
+    oracle's on the same inputs (the device-generated scene is copied to the host and fed to both)."""
+    import torch
+    from deepmerge_b200 import MergeEngine, build_rag
+    from oracle import build as oc
+    from oracle import oracle_np as o
+    R = scene.n_regions
+    L = scene.labels.cpu().numpy()
+    img = scene.image.cpu().numpy()
+    # --- raster stages: plain C restatement
+    k, b, area, per = oc.build_rag(L, R)
+    s, q = oc.pool_bands(L, img, R)
+    rag = build_rag(scene.labels, R, scene.image)
+    assert np.array_equal(rag.edge_keys.cpu().numpy().view(np.uint64), k)
+    assert np.array_equal(rag.boundary_len.cpu().numpy().view(np.uint32), b)
+    assert np.array_equal(rag.area.cpu().numpy(), area) and np.array_equal(rag.perimeter.cpu().numpy(), per)
+    assert np.array_equal(rag.band_sum.cpu().numpy().view(np.uint64), s)
+    assert np.array_equal(rag.band_sumsq.cpu().numpy().view(np.uint64), q)
+    del rag, s, q, img
+    # --- graph stages: numpy restatement (membership, np.mean-order pooling, L2 scores, merge loop)
+    rop = L[scene.ys.cpu().numpy(), scene.xs.cpu().numpy()]
+    assert np.array_equal(scene.region_of_point.cpu().numpy(), rop)
+    feats = scene.feats.cpu().numpy()
+    off, ids = o.csr_from_region_of_point(rop, R)
+    ps, cnt, _ = o.pool_points_csr(off, ids, feats)
+    want = o.merge_graph(ps, cnt, area, per, k, b, tau=0.5)
+    want_labels = oc.relabel(L, want["root"])
+    eng = MergeEngine(H, W, R, feats.shape[1], C=C, n_points=feats.shape[0], device=cuda)
+    got = eng.run(scene.labels, scene.feats, 0.5, image=scene.image, xs=scene.xs, ys=scene.ys)
+    assert got.rounds == want["rounds"] and got.merges == want["merges"]
+    assert np.array_equal(got.root.cpu().numpy(), want["root"])
+    assert np.array_equal(got.labels.cpu().numpy(), want_labels)                  # final label map, 1e8 pixels, bit exact
+    roots = want["root"] == np.arange(R)
+    assert np.array_equal(got.area.cpu().numpy()[roots], want["area"][roots])
+    assert np.array_equal(got.perimeter.cpu().numpy()[roots], want["perim"][roots])
+    E = len(want["keys"])
+    assert np.array_equal(got.edge_keys.cpu().numpy().view(np.uint64), want["keys"])
+    assert np.array_equal(got.boundary_len.cpu().numpy().view(np.uint32)[:E], want["blen"])
+    assert np.array_equal(got.cnt.cpu().numpy()[roots], want["cnt"][roots])
+    np.testing.assert_allclose(got.scores.cpu().numpy()[:E], want["scores"], rtol=1e-3, atol=1e-4)

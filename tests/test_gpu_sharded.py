@@ -1,6 +1,10 @@
-"""GPU: the sharded engine with 2 and 3 virtual ranks emulated as THREADS of one process on one GPU
-(a fake torch.distributed whose collectives meet on host barriers; no kernel ever waits on another
-kernel), compared with the single-GPU engine and with the oracle."""
+"""GPU: the sharded engine (a) with 2, 3 and 4 virtual ranks emulated as THREADS of one process on one GPU (a fake
+torch.distributed whose collectives meet on host barriers; no kernel ever waits on another kernel) and (b), when the
+box has at least two GPUs, as real torchrun-launched processes over NCCL (tests/sharded_nccl_worker.py) -- compared
+with the single-GPU engine and with the oracle."""
+import os
+import subprocess
+import sys
 import threading
 
 import numpy as np
@@ -131,3 +135,18 @@ def test_sharded_row_slot_overflow_is_reported(cuda):
     [t.start() for t in threads]
     [t.join() for t in threads]
     assert len(errors) == world and all("slot overflow" in e for e in errors), errors
+
+
+def test_real_nccl_ranks_equal_the_oracle(cuda):
+    """One process per GPU over real NCCL (torchrun, 2 ranks; 4 when the box has them): label tiles, root table, rounds,
+    merges, merged areas and the gathered edge list equal the oracle's."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs (run with gpurun --gpus 2)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    for world in ([2, 4] if n >= 4 else [2]):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                            "--master-addr", "127.0.0.1", "--master-port", str(29613 + world),
+                            os.path.join(here, "sharded_nccl_worker.py")], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "NCCL PARITY OK" in r.stdout, (world, r.stdout[-2000:], r.stderr[-2000:])

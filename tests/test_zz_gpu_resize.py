@@ -1,9 +1,6 @@
 """GPU: the patch resize of N1 (dm_resize_area) against the oracle restatement of cv2's INTER_AREA and the golden
 outputs of the executed reference (ExtractFeatureDataset.resize_data, MyUtils2.py:362-376).  Bit exact.
-
-The kernel was written after this round's GPU budget was spent: until its first run on hardware the tests are marked
-xfail(strict=False) -- they report XPASS when the kernel is right and cannot turn the suite red when it is not.  The
-file sorts last so that nothing runs after it."""
+"""
 import os
 
 import numpy as np
@@ -11,7 +8,7 @@ import pytest
 
 from oracle.resize_area import resize_data
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="dm_resize_area has not run on hardware yet")]
+pytestmark = pytest.mark.gpu
 
 
 def test_resize_windows_matches_the_executed_reference(cuda, golden_dir):
