@@ -27,7 +27,12 @@ def _dev():
 
 
 def Euclidean_distance(X, Y):
-    """X n*p, Y m*p -> D n*m with D[i,j] = sqrt(max(0, |X_i|^2 + |Y_j|^2 - 2 X_i.Y_j)), float32."""
+    """X n*p, Y m*p -> D n*m with D[i,j] = sqrt(max(0, |X_i|^2 + |Y_j|^2 - 2 X_i.Y_j)).
+
+    The arithmetic is float32 (what the reference computes for its float32 embeddings, ExtractFeatures.py:139-147).  The
+    RESULT dtype follows the reference: float64 inputs give a float64 array -- holding values computed in float32, which
+    is the one documented difference: the reference would carry float64 precision for float64 inputs."""
+    out_dtype = np.result_type(np.asarray(X).dtype, np.asarray(Y).dtype, np.float32)
     X = np.ascontiguousarray(X, dtype=np.float32)
     Y = np.ascontiguousarray(Y, dtype=np.float32)
     if X.ndim != 2 or Y.ndim != 2 or X.shape[1] != Y.shape[1]:
@@ -37,7 +42,7 @@ def Euclidean_distance(X, Y):
     x, y = torch.from_numpy(X).to(dev), torch.from_numpy(Y).to(dev)
     out = torch.empty((X.shape[0], Y.shape[0]), dtype=torch.float32, device=dev)
     L.check(L.dm_euclidean_matrix(_p(x), _p(y), X.shape[0], Y.shape[0], X.shape[1], _p(out), _stream()), "dm_euclidean_matrix")
-    return out.cpu().numpy()
+    return out.cpu().numpy().astype(out_dtype, copy=False)
 
 
 def MC_Lyu_2020(X, Y):
@@ -66,12 +71,26 @@ def region_of_point(point_id_fields, n_points, sep=" "):
     return rop
 
 
+def check_ids(point_ids, n_rows, left_ids, right_ids, n_polygons):
+    """The kernels gather store rows by PointID and mean rows by polygon id without bounds tests: check on the host,
+    and raise as the reference's GetFeaturesByID does for a row outside the store (ExtractFeatures.py:109-112)."""
+    ids = np.asarray(point_ids).ravel()
+    if ids.size and (int(ids.min()) < 0 or int(ids.max()) >= n_rows):
+        bad = int(ids.max()) if int(ids.max()) >= n_rows else int(ids.min())
+        raise IndexError("PointID %d is outside the feature store (%d rows)" % (bad, n_rows))
+    lr = np.concatenate([np.asarray(left_ids, np.int64).ravel(), np.asarray(right_ids, np.int64).ravel()])
+    if lr.size and (int(lr.min()) < 0 or int(lr.max()) >= n_polygons):
+        bad = int(lr.max()) if int(lr.max()) >= n_polygons else int(lr.min())
+        raise IndexError("LEFT_FID / RIGHT_FID %d is not a polygon id (%d polygons)" % (bad, n_polygons))
+
+
 def pool_and_score(store, point_id_fields, left_ids, right_ids):
     """Mean-pool every polygon's member rows of the feature store (np.mean(axis=0) semantics, bit
     exact) and score every (left, right) edge with the Euclidean distance -> (means [R,D] float32,
     simi [E] float64, what the reference writes to the 'simi' OFTReal field :217-219)."""
-    dev = _dev()
     off, ids = membership_csr(point_id_fields)
+    check_ids(ids, int(np.shape(store)[0]), left_ids, right_ids, len(point_id_fields))
+    dev = _dev()
     store = np.ascontiguousarray(store, dtype=np.float32)
     with warnings.catch_warnings():                      # a read-only memory map is fine: the rows are only copied to the device
         warnings.simplefilter("ignore", UserWarning)

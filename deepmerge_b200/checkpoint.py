@@ -34,11 +34,15 @@ def save(path, net, optimizer, epoch, elapsed):
     return path
 
 
-def load(path, net=None, optimizer=None, map_location="cpu", strict=True):
+def load(path, net=None, optimizer=None, map_location="cpu", strict=True, trusted=False):
     """torch.load + `net.load_state_dict(ckpt['net'])` (+ optimizer) as the reference's resume code does.
     A bare state_dict (the reference's `weights` path, Train_SMT.py:182-188) is accepted as well.
-    -> the checkpoint dictionary (epoch, time, ... for the caller)."""
-    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    -> the checkpoint dictionary (epoch, time, ... for the caller).
+
+    The dictionary only holds state_dicts, numbers, lists and strings, so it is read with the safe loader
+    (weights_only=True: no pickle code runs).  trusted=True falls back to the full unpickler for legacy files that hold
+    other objects -- only for files whose origin you trust."""
+    ckpt = torch.load(path, map_location=map_location, weights_only=not trusted)
     if not (isinstance(ckpt, dict) and "net" in ckpt):
         ckpt = {"net": ckpt, "optimizer": None, "epoch": -1, "time": 0.0, "scales": None, "depth": None, "name": None}
     if net is not None:

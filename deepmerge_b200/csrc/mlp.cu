@@ -98,13 +98,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, unsigned parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded: a lost signal must become an error code, not a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity, int* status) {
+// Bounded, without a trap: a lost signal must become an error CODE -- not a hung GPU and not a dead context.  When a
+// wait expires the thread raises the CTA's abort flag (shared memory) and the status word behind the packed weights
+// (global memory: 1 = a bounded wait expired, the outputs are invalid); every other wait that does not succeed at
+// once sees the flag and returns, every role leaves its tile loop at the next tile, and the kernel ends normally.
+// The host reads the status word at its next synchronisation (PackedMLP.check / dm_mlp_status_offset).
+struct Bail {
+    uint32_t flag;     // shared-memory address of the CTA's abort flag
+    int* status;
+};
+__device__ __forceinline__ bool aborted(const Bail& b) {
+    unsigned v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(b.flag) : "memory");
+    return v != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, unsigned parity, const Bail& b) {
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (aborted(b)) return;
         if (++spins > (1u << 20)) {
-            atomicExch(status, 1);
-            __trap();
+            asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(b.flag), "r"(1u) : "memory");
+            atomicExch(b.status, 1);
+            return;
         }
     }
 }
@@ -188,6 +203,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* bias = (float*)(smem + OFF_BIAS);
     uint32_t* tmem_slot = (uint32_t*)(smem + OFF_TMEM);
+    const Bail bail{sbase + OFF_TMEM + 4u, P.status};           // the abort flag sits beside the TMEM base address
     const uint32_t bar0 = sbase + OFF_BARS;
     auto full_b = [&](int s) { return bar0 + 8u * s; };
     auto full_a = [&](int s) { return bar0 + 8u * (STAGES + s); };
@@ -209,6 +225,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
         for (int i = threadIdx.x; i < (W3_BYTES + BIAS_FLOATS * 4) / 16; i += THREADS) dst[i] = src[i];
     }
     if (threadIdx.x == 0) {
+        tmem_slot[1] = 0;                     // abort flag
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_b(s), 1);
             mbar_init(full_a(s), PROD_WARPS);
@@ -238,9 +255,9 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
     if (warp == 0) {
         // ===== weight loader =====================================================================
         Ring ring;
-        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int64_t tile = blockIdx.x; tile < tiles && !aborted(bail); tile += gridDim.x) {
             for (int kc = 0; kc < nk1 + nk2; ++kc) {
-                mbar_wait(empty(ring.stage), ring.phase ^ 1u, P.status);
+                mbar_wait(empty(ring.stage), ring.phase ^ 1u, bail);
                 if (lane == 0) {
                     // W1 chunks in order, then W2 chunks in the order the epilogue halves finish them: 0, 2, 1, 3
                     const int ck = kc < nk1 ? kc : nk1 + kc_order(kc - nk1);
@@ -262,8 +279,8 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
         constexpr uint32_t idesc_hid = umma_idesc(M_TILE, N_HID), idesc_out = umma_idesc(M_TILE, N_OUT);
         auto issue_l1 = [&]() {           // D1 = X W1^T, both operands from the ring
             for (int kc = 0; kc < nk1; ++kc) {
-                mbar_wait(full_b(ring.stage), ring.phase, P.status);
-                mbar_wait(full_a(ring.stage), (fa_bits >> ring.stage) & 1u, P.status);
+                mbar_wait(full_b(ring.stage), ring.phase, bail);
+                mbar_wait(full_a(ring.stage), (fa_bits >> ring.stage) & 1u, bail);
                 fa_bits ^= 1u << ring.stage;
                 tc_fence_after();
                 if (lane == 0) {
@@ -280,12 +297,12 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
         };
         if ((int64_t)blockIdx.x < tiles) issue_l1();
         unsigned it = 0;
-        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        for (int64_t tile = blockIdx.x; tile < tiles && !aborted(bail); tile += gridDim.x, ++it) {
             // layer 2: D2 = h1 W2^T, A from the resident activation buffer, B from the ring
             for (int i = 0; i < nk2; ++i) {
                 const int kc = kc_order(i);                               // h1 chunk kc is ready as soon as its half wrote it
-                mbar_wait(a1_ready(kc), it & 1u, P.status);
-                mbar_wait(full_b(ring.stage), ring.phase, P.status);
+                mbar_wait(a1_ready(kc), it & 1u, bail);
+                mbar_wait(full_b(ring.stage), ring.phase, bail);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a0 = sbase + OFF_A2 + kc * A_CHUNK_BYTES;
@@ -302,7 +319,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
             if (tile + gridDim.x < tiles) issue_l1();          // next tile's layer 1 overlaps this tile's epilogue 2
             // layer 3: D3 = h2 W3^T, both operands resident; D3 takes over D2's columns (E2 has read them)
             // (D3 overwrites D2's first 16 columns: wait for ALL of epilogue 2 before the first layer-3 MMA)
-            for (int i = 0; i < nk2; ++i) mbar_wait(a2_ready(i), it & 1u, P.status);
+            for (int i = 0; i < nk2; ++i) mbar_wait(a2_ready(i), it & 1u, bail);
             tc_fence_after();
             if (lane == 0) {
                 for (int kc = 0; kc < nk2; ++kc) {
@@ -322,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
         constexpr int RPW = M_TILE / PROD_WARPS;      // rows per producer warp
         constexpr int ITS = RPW / 4;                  // 4 rows per warp instruction (8 lanes x 16 bytes per row chunk)
         const int piece = lane & 7, rsub = lane >> 3; // 16-byte piece / row within a 4-row group
-        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int64_t tile = blockIdx.x; tile < tiles && !aborted(bail); tile += gridDim.x) {
             const int64_t row0 = tile * M_TILE;
             // rows this thread gathers: w*RPW + it*4 + rsub
             const float* base_lo[ITS];
@@ -344,7 +361,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
             const int D = P.keys ? P.D : P.in_features, K = P.in_features;
             const bool vec4 = (D % 4 == 0) && (K % 4 == 0) && (P.ld % 4 == 0) && (((uintptr_t)P.src & 15) == 0);
             for (int kc = 0; kc < nk1; ++kc) {
-                mbar_wait(empty(ring.stage), ring.phase ^ 1u, P.status);
+                mbar_wait(empty(ring.stage), ring.phase ^ 1u, bail);
                 unsigned char* a_st = smem + OFF_RING + ring.stage * STAGE_BYTES;
                 const int k0 = kc * KC + piece * 8;
 #pragma unroll
@@ -380,7 +397,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
             // layer 2's ring uses carry no A chunk, but the producers still pace themselves on them: running more
             // than one ring round ahead of the MMA warp would alias the mbarrier phase parity
             for (int kc = 0; kc < nk2; ++kc) {
-                mbar_wait(empty(ring.stage), ring.phase ^ 1u, P.status);
+                mbar_wait(empty(ring.stage), ring.phase ^ 1u, bail);
                 ring.advance();
             }
         }
@@ -389,7 +406,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
         const int half = (warp - 2) >> 2;             // which half of the 256 columns this warp handles
         unsigned it = 0;
-        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        for (int64_t tile = blockIdx.x; tile < tiles && !aborted(bail); tile += gridDim.x, ++it) {
             const int64_t row0 = tile * M_TILE;
             const int r = quad * 32 + lane;           // accumulator row of this thread
             const int64_t e = row0 + r;
@@ -397,7 +414,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
             // ---- epilogue 1 / 2: h = lrelu(D + b) -> bf16 A operand (and fp32 h2) ---------------------
 #pragma unroll 1
             for (int layer = 0; layer < 2; ++layer) {
-                mbar_wait(layer == 0 ? d1_full : d2_full, it & 1u, P.status);
+                mbar_wait(layer == 0 ? d1_full : d2_full, it & 1u, bail);
                 tc_fence_after();
                 const float* b = bias + layer * N_HID;
 #pragma unroll 1
@@ -430,7 +447,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_mlp_kernel(const Params P) {
             }
             // ---- epilogue 3: o = lrelu(D3 + b3) ------------------------------------------------------
             // every epilogue warp waits (the next tile's h1 must not overwrite h2 before layer 3 has read it)
-            mbar_wait(d3_full, it & 1u, P.status);
+            mbar_wait(d3_full, it & 1u, bail);
             tc_fence_after();
             if (half == 0) {
                 uint32_t v[16];
@@ -520,6 +537,11 @@ using namespace dm;
 extern "C" size_t dm_mlp_packed_bytes(int64_t in_features, int64_t hidden, int64_t n_out) {
     if (mlp::check_dims(in_features, hidden, n_out) != DM_OK) return 0;
     return mlp::packed_bytes(mlp::nk_for(in_features)) + 16;      // + the status word of the kernel's bounded waits
+}
+
+extern "C" size_t dm_mlp_status_offset(int64_t in_features, int64_t hidden, int64_t n_out) {
+    if (mlp::check_dims(in_features, hidden, n_out) != DM_OK) return 0;
+    return mlp::packed_bytes(mlp::nk_for(in_features));
 }
 
 extern "C" int dm_mlp_pack(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,

@@ -98,10 +98,14 @@ __global__ void __launch_bounds__(256) region_mean_kernel(const float* __restric
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     auto one = [&](int64_t r) {
-        const float c = (float)max(cnt[r], 1);
+        // A region without sample points has no embedding: its mean (and norm) is NaN, what np.mean over no rows gives
+        // (ExtractFeatures.py:211-212; the reference itself raises earlier on an empty PointID field).  NaN scores fail
+        // `< tau`, NaN logits fail `o1 > o0`: such a region never merges on the strength of a made-up zero vector.
+        const int n = cnt[r];
+        const float c = n > 0 ? (float)n : __int_as_float(0x7fc00000);
         float n2 = 0.f;
         for (int d = lane; d < D; d += 32) {
-            const float v = __fdiv_rn(sum[r * D + d], c);
+            const float v = n > 0 ? __fdiv_rn(sum[r * D + d], c) : c;
             mean[r * D + d] = v;
             n2 = __fmaf_rn(v, v, n2);
         }

@@ -307,12 +307,20 @@ class PackedMLP:
         with torch.cuda.device(dev):
             L.check(L.dm_mlp_pack(*[_p(w) for w in ws], self.in_features, self.hidden, self.n_out, _p(self.blob),
                                   _stream()), "dm_mlp_pack")
+        off = L.dm_mlp_status_offset(self.in_features, self.hidden, self.n_out)
+        self.status = self.blob[off:off + 4].view(torch.int32)      # 1 = a bounded wait inside the kernel expired
+
+    def check(self):
+        """Synchronises and raises if the kernel reported a lost signal (its outputs are invalid then)."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("pair-MLP kernel: a bounded wait expired (lost TMA / tensor-core signal); outputs are invalid")
 
 
-def score_mlp(mean, edge_keys, mlp: PackedMLP, want_h2=False, n_edges_dev=None, out=None):
+def score_mlp(mean, edge_keys, mlp: PackedMLP, want_h2=False, n_edges_dev=None, out=None, check=False):
     """Pair-MLP scores of every edge: x_e = concat(mean[lo], mean[hi]) through the three
     Linear + leaky_relu layers of Nets.MLP.forward (Nets.py:28-35), bf16 operands / fp32
-    accumulation on tcgen05 -> (o fp32 [E, n_out], h2 fp32 [E, hidden] or None)."""
+    accumulation on tcgen05 -> (o fp32 [E, n_out], h2 fp32 [E, hidden] or None).
+    Asynchronous; check=True synchronises and raises if the kernel reported a lost signal (mlp.check())."""
     L = lib()
     _need_cuda(mean, edge_keys)
     if mean.dtype != _F32 or not mean.is_contiguous():
@@ -328,10 +336,12 @@ def score_mlp(mean, edge_keys, mlp: PackedMLP, want_h2=False, n_edges_dev=None, 
         n = n_edges_dev if n_edges_dev is not None else torch.tensor([E], dtype=_I64, device=dev)
         L.check(L.dm_score_mlp_bf16(_p(mean), D, _p(edge_keys.contiguous()), _p(n), E, _p(mlp.blob), mlp.in_features,
                                     mlp.hidden, mlp.n_out, _p(o), _p(h2), _stream()), "dm_score_mlp_bf16")
+    if check:
+        mlp.check()
     return o, h2
 
 
-def mlp_forward(x, mlp: PackedMLP, want_h2=True):
+def mlp_forward(x, mlp: PackedMLP, want_h2=True, check=False):
     """Nets.MLP()(x): x fp32 [B, in_features] -> (fc3 [B, n_out], fc2 [B, hidden])."""
     L = lib()
     _need_cuda(x)
@@ -344,6 +354,8 @@ def mlp_forward(x, mlp: PackedMLP, want_h2=True):
     with torch.cuda.device(x.device):
         L.check(L.dm_mlp_forward_bf16(_p(x), B, _p(mlp.blob), K, mlp.hidden, mlp.n_out, _p(o), _p(h2), _stream()),
                 "dm_mlp_forward_bf16")
+    if check:
+        mlp.check()
     return o, h2
 
 
@@ -551,6 +563,11 @@ class MergeEngine:
                 self.logits = torch.empty((cap, mlp.n_out), dtype=_F32, device=self.dev)
             L.check(L.dm_score_mlp_bf16(_p(self.mean), D, _p(self.keys), _p(n_edges), cap, _p(mlp.blob), mlp.in_features,
                                         mlp.hidden, mlp.n_out, _p(self.logits), None, s), "dm_score_mlp_bf16")
+            self.counts[3:4].add_(self.mlp_status_shift(mlp))       # the kernel's status word travels with the round's read-back
+
+    @staticmethod
+    def mlp_status_shift(mlp):
+        return mlp.status.to(_I64) << 1                            # counts[3]: 1 = bad label, >= 2 = internal error
 
     def _merge_init(self):
         """parent = identity, everything alive, round counters zero (run() does this beside the raster pass)."""
@@ -587,6 +604,8 @@ class MergeEngine:
                     raise RuntimeError("dm_rag_build: internal pipeline error")
                 if c[2] != 0:
                     raise OverflowError(int(c[1]))
+            if c[3] > 1:
+                raise RuntimeError("pair-MLP kernel: a bounded wait expired (lost TMA / tensor-core signal)")
             merges += int(c[5])                       # members absorbed by the previous round
             if c[4] == 0 or rounds == max_rounds:
                 break

@@ -97,6 +97,8 @@ class ShardedMergeEngine:
         from .raster import MergeEngine, default_edge_capacity
         self.dist, self.group = dist, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 31:          # every rank checks alike: the rank-visibility masks are 31 bits of an int32
+            raise ValueError("ShardedMergeEngine supports at most 31 ranks (got %d)" % self.world)
         self.H, self.W = H, W
         self.row_capacity = row_capacity
         self.y0, self.y1 = tile_bounds(H, self.world, self.rank)
@@ -137,8 +139,11 @@ class ShardedMergeEngine:
         self.slot_n = self.slot[:8].view(torch.int64)
         self.slot_ids = self.slot[16:16 + 4 * self.row_cap].view(torch.int32)
         self.slot_rows = self.slot[16 + 4 * self.row_cap:16 + 4 * self.row_cap * (D + 1)].view(torch.float32).view(self.row_cap, D)
-        self.flags = z(4, dt=torch.int64)                          # [0] selected (global), [1] parent changed, [2] slot overflow
-        self.host_flags = torch.zeros(4, dtype=torch.int64).pin_memory()
+        # [0] selected, [1] parent changed, [2] row-slot overflow, [3] tile edge-list overflow, [4] bad label, [5] internal
+        # error, [6] raw entries needed -- [0] and [2:7] are all-reduced with MAX once per round, so that every rank raises
+        # (or goes on) together: a rank that left the loop alone would leave its peers hanging in the next collective
+        self.flags = z(8, dt=torch.int64)
+        self.host_flags = torch.zeros(8, dtype=torch.int64).pin_memory()
 
     def _exchange_rows(self, flag, add):
         """Ship the embedding sums of the flagged regions to every rank: pack -> all_gather (fixed slots + device
@@ -147,9 +152,11 @@ class ShardedMergeEngine:
         e, L, dist, s = self.eng, self.eng.L, self.dist, _stream()
         L.check(L.dm_rows_pack(_p(flag), _p(e.sum), e.R, e.D, _p(self.slot_ids), _p(self.slot_rows), self.row_cap,
                                _p(self.slot_n), s), "dm_rows_pack")
-        self.flags[2:3].copy_(torch.maximum(self.flags[2:3], (self.slot_n > self.row_cap).to(torch.int64)))
         g = all_gather_slots(self.slot, dist, self.group).view(self.world, self.slot_bytes)
         rc = self.row_cap
+        # a slot that overflowed on ANY rank is seen by every rank in the gathered counts: all of them flag it
+        over = (g[:, :8].contiguous().view(torch.int64) > rc).any().to(torch.int64).reshape(1)
+        self.flags[2:3].copy_(torch.maximum(self.flags[2:3], over))
         g_n = [g[r, :8].view(torch.int64) for r in range(self.world)]
         g_ids = [g[r, 16:16 + 4 * rc].view(torch.int32) for r in range(self.world)]
         g_rows = [g[r, 16 + 4 * rc:16 + 4 * rc * (e.D + 1)].view(torch.float32) for r in range(self.world)]
@@ -217,13 +224,17 @@ class ShardedMergeEngine:
                 L.check(L.dm_merge_select_l2(_p(e.scores), float(tau), _p(n_edges), cap, _p(e.selected),
                                              e.counts[4:5].data_ptr(), s), "dm_merge_select_l2")
                 self.flags[0:1].copy_(e.counts[4:5])
-                dist.all_reduce(self.flags[0:1], op=SUM, group=grp)
+                if rounds == 0:                                     # this rank's tile-pass conditions travel with the count
+                    self.flags[3:4].copy_((e.counts[2:3] != 0).to(torch.int64))
+                    self.flags[4:5].copy_((e.counts[3:4] == 1).to(torch.int64))
+                    self.flags[5:6].copy_((e.counts[3:4] > 1).to(torch.int64))
+                    self.flags[6:7].copy_(e.counts[1:2])
+                dist.all_reduce(self.flags, op=MAX, group=grp)      # one collective: "any rank selected" + every error flag
                 f, c = self._read_flags()
-                if rounds == 0:
-                    if c[3] == 1:
-                        raise ValueError("labels contain ids >= n_regions")
-                    if c[3] != 0 or c[2] != 0:
-                        raise RuntimeError("tile edge list overflow / pipeline error (capacity %d, needed %d)" % (cap, c[1]))
+                if f[4] != 0:
+                    raise ValueError("labels contain ids >= n_regions")
+                if f[5] != 0 or f[3] != 0:
+                    raise RuntimeError("tile edge list overflow / pipeline error (capacity %d, needed %d)" % (cap, f[6]))
                 if f[2] != 0:
                     raise RuntimeError("row exchange slot overflow (row_cap %d)" % self.row_cap)
                 merges += int(c[5])

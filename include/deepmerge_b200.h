@@ -149,7 +149,9 @@ int dm_csr_build(const int32_t* region_of_point, int64_t n_points, int64_t n_reg
                  int32_t* point_ids, void* ws, size_t ws_bytes, dm_stream_t stream);
 int dm_pool_points_csr(const int64_t* offsets, const int32_t* point_ids, const float* feats, int64_t feat_ld,
                        int64_t n_regions, int64_t D, float* sum, int32_t* cnt, dm_stream_t stream);
-/* mean[r] = sum[r] / max(cnt[r],1) (IEEE fp32 division), norm2[r] = sum_d mean[r,d]^2.
+/* mean[r] = sum[r] / cnt[r] (IEEE fp32 division), norm2[r] = sum_d mean[r,d]^2.  A region without sample points
+ * (cnt[r] == 0) gets mean = norm2 = NaN -- what np.mean over no rows gives -- so that its edges score NaN
+ * (dm_score_l2) / NaN logits (dm_score_mlp_bf16) and are never selected by dm_merge_select_*.
  * `only` (nullable) restricts the update to regions with only[r] != 0. */
 int dm_region_mean(const float* sum, const int32_t* cnt, int64_t n_regions, int64_t D, float* mean,
                    float* norm2, const uint8_t* only, dm_stream_t stream);
@@ -209,8 +211,12 @@ int dm_euclidean_matrix(const float* X, const float* Y, int64_t n, int64_t m, in
  *     with TMEM accumulators.  Weights are fp32 row-major [out_features, in_features] as in
  *     torch.nn.Linear; dm_mlp_pack converts them once into the padded bf16 UMMA layout.
  *     o [E, n_out] fp32; h2 (nullable) [E, hidden] fp32.
- * ----------------------------------------------------------------------------------- */
+ *     Every wait inside the kernel is bounded.  A wait that expires (a lost TMA / tensor-core signal) neither hangs nor
+ *     traps: the CTA abandons its remaining tiles and the int32 STATUS WORD at byte dm_mlp_status_offset(...) of the
+ *     packed blob becomes 1 (outputs invalid).  dm_mlp_pack clears it; read it after synchronising the stream.
+ */
 size_t dm_mlp_packed_bytes(int64_t in_features, int64_t hidden, int64_t n_out);
+size_t dm_mlp_status_offset(int64_t in_features, int64_t hidden, int64_t n_out);
 int dm_mlp_pack(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                 const float* b3, int64_t in_features, int64_t hidden, int64_t n_out, void* packed,
                 dm_stream_t stream);

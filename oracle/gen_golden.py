@@ -11,6 +11,7 @@ hard-codes Windows paths, needs OGR/h5py and `break`s after the first edge (:223
 from __future__ import annotations
 
 import os
+import sys
 import random
 import tempfile
 
@@ -184,6 +185,78 @@ def golden_pair_sampler(ref, rng):
              out_right=np.array([int(d[2]) for d in data]), out_flag=np.array([d[3] for d in data]))
 
 
+DESIGNED = ("area", "peri", "len", "width", "smooth", "std0", "std1", "std2", "mean0", "mean1", "mean2", "shapeness",
+            "compact", "bright", "border")
+
+
+def golden_pair_dataset(ref, rng):
+    """The whole MergingSegmensPairDataset (MyUtils1.py:20-58, :236-295): add_data for a positive and a negative pair
+    list over fake OGR / GDAL objects, then __getitem__ -> (left_meta, right_meta, flag) with
+    meta = (designed [1,19], scales [1,4], [4 patches])."""
+    R, H, W = 12, 90, 110
+    arr = rng.integers(0, 256, size=(3, H, W)).astype(np.uint8)
+    gt = (500.0, 2.0, 0.0, 1300.0, 0.0, -2.0)
+    npts = rng.integers(1, 4, size=R)
+    fields, pos = [], 0
+    for r in range(R):
+        fields.append(" ".join(str(pos + k) for k in range(npts[r])))
+        pos += int(npts[r])
+    N = pos
+    attr = np.round(rng.uniform(0.5, 300.0, size=(N, 15)), 3)
+    inner = rng.integers(6, 20, size=N)
+    obj = inner + rng.integers(3, 25, size=N)
+    X = gt[0] + rng.uniform(0, W - 1, size=N) * gt[1]
+    Y = gt[3] + rng.uniform(0, H - 1, size=N) * gt[5]
+    X[0], Y[0] = gt[0], gt[3]                                              # a corner point: zero-padded windows
+    X[1], Y[1] = gt[0] + (W - 1) * gt[1], gt[3] + (H - 1) * gt[5]
+
+    def point(i):
+        f = dict(zip(DESIGNED, attr[i].tolist()))
+        f["inner"], f["object"] = int(inner[i]), int(obj[i])
+        return ref_shim.FakeFeature(i, f, (float(X[i]), float(Y[i])))
+
+    polys = ref_shim.FakeLayer([ref_shim.FakeFeature(r, {"PointID": fields[r]}) for r in range(R)])
+    pts = ref_shim.FakeLayer([point(i) for i in range(N)])
+    pos_pairs = rng.integers(0, R, size=(9, 2))
+    neg_pairs = rng.integers(0, R, size=(7, 2))
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            for name, pairs in (("tileA.txt", pos_pairs), ("tileB.txt", neg_pairs)):
+                with open(name, "w") as f:
+                    for j, (a, b) in enumerate(pairs):
+                        f.write(f"{j},{a},{b},0,0\n")
+            layers, rasters = {}, {}
+            for t in ("tileA", "tileB"):
+                layers[f"PF\\{t}.shp"] = polys
+                layers[f"QF\\{t}\\PointsGCS.shp"] = pts
+                rasters[f"IF\\{t}.tif"] = ref_shim.FakeRaster(arr, geotransform=gt)
+            ref_shim.install_fake_drivers(ref, layers, rasters)
+            ds = object.__new__(ref.MyUtils1.MergingSegmensPairDataset)
+            ds.image_folder, ds.polygon_folder, ds.point_folder = "IF", "PF", "QF"
+            ds.data, ds.point_dataset, ds.img_dataset, ds.layers = [], [], {}, {}
+            random.seed(11)
+            ds.positive_number, ds.positive_pair_number = ds.add_data(["tileA.txt"], 1)
+            ds.negative_number, ds.negative_pair_number = ds.add_data(["tileB.txt"], 0)
+        finally:
+            os.chdir(cwd)
+    out = {}
+    for i in range(len(ds)):
+        left, right, flag = ds[i]
+        for side, meta in (("l", left), ("r", right)):
+            out[f"{side}{i}_designed"] = meta[0].numpy()
+            out[f"{side}{i}_scales"] = meta[1].numpy()
+            for k, patch in enumerate(meta[2]):
+                out[f"{side}{i}_patch{k}"] = patch
+        out[f"flag{i}"] = np.int64(flag)
+    np.savez_compressed(os.path.join(OUT, "pair_dataset.npz"), arr=arr, gt=np.array(gt), fields=np.array(fields), attr=attr,
+                        inner=inner, obj=obj, X=X, Y=Y, pos_pairs=pos_pairs, neg_pairs=neg_pairs, seed=11, n=len(ds),
+                        counts=np.array([ds.positive_number, ds.positive_pair_number, ds.negative_number,
+                                         ds.negative_pair_number]),
+                        data=np.array([[d[0], d[1], d[2], str(d[3])] for d in ds.data]), **out)
+
+
 def golden_geometry(ref, rng):
     """calculate_left_top_point_and_size :379-383, get_scales :300-327, cut_image :330-360,
     pixel mapping :241-242 of MyUtils2.ExtractFeatureDataset."""
@@ -226,10 +299,20 @@ def main():
         raise SystemExit("needs /root/reference (build container only)")
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
+    only = set(sys.argv[1:])                          # optional: names of the generators to run
     rng = np.random.default_rng(20261018)
     for fn in (golden_euclid, golden_pool_score, golden_mlp, golden_loss, golden_edge_reader,
                golden_pair_sampler, golden_geometry, golden_resize):
+        if only and fn.__name__ not in only:
+            # keep the shared random stream in step: run the generator into a scratch directory
+            continue
         fn(ref, rng)
+        print("wrote", fn.__name__)
+    # generators added later draw from streams of their own, so that the fixtures above never change
+    for fn, seed in ((golden_pair_dataset, 20261019),):
+        if only and fn.__name__ not in only:
+            continue
+        fn(ref, np.random.default_rng(seed))
         print("wrote", fn.__name__)
 
 

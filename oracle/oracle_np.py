@@ -314,7 +314,7 @@ def pool_points_csr(offsets, point_ids, feats):
     """Region pooling, ExtractFeatures.py:188-212: rows gathered in PointID order and
     reduced with np.mean(axis=0), i.e. sequential fp32 row accumulation then one fp32
     division by n.  Returns (sum fp32 [R,D], cnt int32 [R], mean fp32 [R,D]); a region
-    with no points has sum = mean = 0 (the reference would raise on int(''))."""
+    with no points has sum = 0 and mean = NaN (see region_mean)."""
     offsets = np.asarray(offsets, np.int64)
     R = offsets.shape[0] - 1
     D = feats.shape[1]
@@ -327,8 +327,14 @@ def pool_points_csr(offsets, point_ids, feats):
 
 
 def region_mean(sum_, cnt):
-    c = np.maximum(np.asarray(cnt), 1).astype(np.float32)[:, None]
-    return (sum_.astype(np.float32) / c).astype(np.float32)
+    """np.mean(rows, axis=0) per region (ExtractFeatures.py:211-212).  A region without sample points has no embedding
+    (the reference cannot reach this case: int('') on an empty PointID field raises, :190): its mean is NaN -- what
+    np.mean over no rows gives -- so its edges score NaN and are never selected (spec of this build)."""
+    c = np.asarray(cnt).astype(np.float32)[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        m = (sum_.astype(np.float32) / c).astype(np.float32)
+    m[np.asarray(cnt) <= 0] = np.nan
+    return m
 
 
 def pool_dense(labels, emb, n_regions):

@@ -84,7 +84,8 @@ def test_merge_is_deterministic_idempotent_and_consistent(cuda, scene):
     E = a.edge_keys.shape[0]
     assert torch.equal(again.edge_keys, a.edge_keys) and torch.equal(again.boundary_len, a.boundary_len[:E])
     # no surviving edge is below the threshold (the loop ran to its fixed point)
-    assert a.rounds < 64 and bool((a.scores >= 0.5).all())
+    # (a region without sample points has a NaN embedding: its edges score NaN and are never selected)
+    assert a.rounds < 64 and not bool((a.scores < 0.5).any())
 
 
 def test_whole_step_against_the_oracle_at_full_size(cuda, scene):

@@ -115,3 +115,61 @@ def test_test_for_shp_on_real_shapefiles(cuda, golden_dir, tmp_path, capsys):
     keep = np.arange(len(left)) != 7
     assert np.isnan(col[7])
     np.testing.assert_allclose(col[keep], p["simi"][keep], rtol=1e-3)
+
+
+def test_pair_dataset_items_equal_the_executed_reference(cuda, golden_dir, tmp_path):
+    """ds[i] -> (left_meta, right_meta, flag), meta = (designed [1,19], scales [1,4], [4 patches]): every item of the
+    executed reference class (MyUtils1.py:41-80, patches through cv2 INTER_AREA) bit for bit, and batch() == items."""
+    import random
+    import torch
+    from deepmerge_b200 import MyUtils1
+    from test_mirrors_cpu import _pair_dataset_fixture
+    g = np.load(os.path.join(golden_dir, "pair_dataset.npz"))
+    pos, neg, open_vector, open_image = _pair_dataset_fixture(g, tmp_path)
+    random.seed(int(g["seed"]))
+    ds = MyUtils1.MergingSegmensPairDataset("IF", "PF", "QF", pos, neg, open_vector=open_vector, open_image=open_image,
+                                            device=cuda)
+    n = int(g["n"])
+    for i in range(n):
+        left, right, flag = ds[i]
+        assert flag == int(g[f"flag{i}"])
+        for side, meta in (("l", left), ("r", right)):
+            assert isinstance(meta[0], torch.Tensor) and tuple(meta[0].shape) == (1, 19) and tuple(meta[1].shape) == (1, 4)
+            assert np.array_equal(meta[0].numpy(), g[f"{side}{i}_designed"])
+            assert np.array_equal(meta[1].numpy(), g[f"{side}{i}_scales"])
+            for k in range(4):
+                assert meta[2][k].dtype == np.float32 and np.array_equal(meta[2][k], g[f"{side}{i}_patch{k}"]), (i, side, k)
+    b = ds.batch(range(n))
+    assert b["flag"].tolist() == [int(g[f"flag{i}"]) for i in range(n)]
+    for side, key in (("l", "left"), ("r", "right")):
+        designed, scales, patches = b[key]
+        assert np.array_equal(designed.cpu().numpy(), np.concatenate([g[f"{side}{i}_designed"] for i in range(n)]))
+        for k in range(4):
+            assert np.array_equal(patches[k].cpu().numpy(), np.stack([g[f"{side}{i}_patch{k}"] for i in range(n)]))
+
+
+def test_join_adjacency_drives_the_merge_loop(cuda):
+    """R2: the polygon `join` fields (MyUtils.py:110-114, neighbour ids including self) parsed by edge_keys_from_join give
+    the graph build_rag extracts from the raster; merge_graph on it equals the oracle."""
+    import torch
+    from deepmerge_b200 import MyUtils, merge_graph
+    from oracle import oracle_np as o
+    sc = o.synth_scene(160, 256, 260, C=4)
+    R = sc["n_regions"]
+    keys, blen, area, per = o.build_rag(sc["labels"], R)
+    lo, hi = o.unpack_keys(keys)
+    nb = [[r] for r in range(R)]
+    for a, b in zip(lo.tolist(), hi.tolist()):
+        nb[a].append(b)
+        nb[b].append(a)
+    join = [",".join(str(v) for v in sorted(l)) for l in nb]                  # the attribute as the reference reads it
+    assert MyUtils.neighbours_from_join(join[5], 5) == sorted(v for v in nb[5] if v != 5)
+    jk = MyUtils.edge_keys_from_join(join)
+    assert np.array_equal(jk.view(np.uint64), keys)
+    off, ids = o.csr_from_region_of_point(sc["region_of_point"], R)
+    ps, cnt, _ = o.pool_points_csr(off, ids, sc["feats"])
+    want = o.merge_graph(ps, cnt, area, per, keys, blen, tau=0.5)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+    got = merge_graph(T(ps), T(cnt), T(area), T(per), T(jk), T(blen.view(np.int32)), 0.5)
+    assert np.array_equal(got.root.cpu().numpy(), want["root"]) and got.rounds == want["rounds"] and got.merges == want["merges"]
+    assert np.array_equal(got.edge_keys.cpu().numpy().view(np.uint64), want["keys"])

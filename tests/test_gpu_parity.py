@@ -277,7 +277,9 @@ def test_pool_points_matches_oracle(cuda, D):
     hs, hc, hm = o.pool_points_csr(ho, hi, feats)
     assert np.array_equal(s.cpu().numpy(), hs) and np.array_equal(c.cpu().numpy(), hc)
     mean, n2 = region_mean(s, c)
-    assert np.array_equal(mean.cpu().numpy(), hm)
+    hm = o.region_mean(hs, hc)                                  # NaN rows for regions without points, as np.mean gives
+    assert (hc == 0).any() and np.isnan(hm[hc == 0]).all()
+    assert np.array_equal(mean.cpu().numpy(), hm, equal_nan=True)
     np.testing.assert_allclose(n2.cpu().numpy(), np.sum(hm.astype(np.float64) ** 2, 1), rtol=1e-5)
 
 
@@ -372,6 +374,41 @@ def test_merge_graph_matches_oracle(cuda, seed, tau):
     assert np.array_equal(got.cnt.cpu().numpy()[roots], want["cnt"][roots])
     assert np.array_equal(got.sum.cpu().numpy()[roots], want["sum"][roots])       # fixed summation order
     np.testing.assert_allclose(got.scores.cpu().numpy(), want["scores"], rtol=1e-3, atol=1e-3)
+
+
+def test_regions_without_sample_points_never_merge(cuda):
+    """A region without points has no embedding (np.mean over no rows is NaN, ExtractFeatures.py:211):
+    its edges score NaN and are never selected -- neither against another empty region (a made-up zero vector would
+    score 0) nor against a low-norm neighbour -- for the L2 scorer and for the pair-MLP."""
+    from deepmerge_b200 import PackedMLP, merge_graph
+    R, D = 6, 4
+    #   0 -- 1 -- 2 -- 3 -- 4 -- 5      1 and 2 are empty, 3 has a tiny embedding, 4 / 5 are close to each other
+    keys = o.pack_keys(np.arange(R - 1), np.arange(1, R))
+    blen = np.ones(R - 1, np.uint32)
+    cnt = np.array([2, 0, 0, 1, 1, 1], np.int32)
+    sum_ = np.zeros((R, D), np.float32)
+    sum_[0] = 6.0
+    sum_[3] = 1e-3
+    sum_[4] = 5.0
+    sum_[5] = 5.01
+    area = np.full(R, 10, np.int64)
+    per = np.full(R, 14, np.int64)
+    want = o.merge_graph(sum_, cnt, area, per, keys, blen, tau=0.5)
+    assert want["merges"] == 1 and np.array_equal(want["root"], [0, 1, 2, 3, 4, 4])       # only 4 -- 5
+    got = merge_graph(T(sum_, cuda), T(cnt, cuda), T(area, cuda), T(per, cuda), T(keys.view(np.int64), cuda),
+                      T(blen.view(np.int32), cuda), 0.5)
+    assert np.array_equal(got.root.cpu().numpy(), want["root"]) and got.merges == 1
+    sc = got.scores.cpu().numpy()
+    assert np.isnan(sc[:3]).all() and np.isfinite(sc[3:]).all()                           # edges 0-1, 1-2, 2-3 have no score
+    # the same with a pair-MLP that says "merge" for EVERY finite input
+    h = 2 * D
+    Wm = [np.zeros((h, 2 * D), np.float32), np.zeros(h, np.float32), np.zeros((h, h), np.float32), np.zeros(h, np.float32),
+          np.zeros((2, h), np.float32), np.array([0.0, 1.0], np.float32)]
+    want = o.merge_graph(sum_, cnt, area, per, keys, blen, mlp=tuple(Wm), mlp_bf16=True, max_rounds=1)
+    got = merge_graph(T(sum_, cuda), T(cnt, cuda), T(area, cuda), T(per, cuda), T(keys.view(np.int64), cuda),
+                      T(blen.view(np.int32), cuda), 0.0, mlp=PackedMLP(*[T(w, cuda) for w in Wm]), max_rounds=1)
+    assert np.array_equal(want["root"], [0, 1, 2, 3, 3, 3])                               # 3 -- 4 -- 5 only
+    assert np.array_equal(got.root.cpu().numpy(), want["root"])
 
 
 def test_merge_graph_max_rounds_and_snake(cuda):

@@ -183,3 +183,67 @@ def test_point_patches_grouping_logic(monkeypatch):
         for i in range(n):
             win = MyUtils2.calculate_left_top_point_and_size(int(w["xpix"][i]), int(w["ylin"][i]), int(scales[i, k]))
             assert np.array_equal(got[k][i].numpy(), resize_data(MyUtils2.cut_image(img, win), cfg)), (i, k)
+
+
+def test_pool_and_score_rejects_ids_outside_the_store_before_touching_the_gpu():
+    """ExtractFeatures.py:109-112: a row outside the feature store is an error in the reference; here the ids are
+    validated on the host because the kernels gather by them without bounds tests."""
+    from deepmerge_b200.ExtractFeatures import check_ids, pool_and_score
+    store = np.zeros((5, 4), np.float32)
+    with pytest.raises(IndexError):
+        pool_and_score(store, ["0 1", "2 7"], [0], [1])                    # PointID 7 >= 5 rows
+    with pytest.raises(IndexError):
+        pool_and_score(store, ["0 1", "2 3"], [0], [2])                    # RIGHT_FID 2: only polygons 0 and 1 exist
+    with pytest.raises(IndexError):
+        check_ids(np.array([-1, 0]), 5, [0], [1], 2)
+    check_ids(np.array([0, 4]), 5, [0, 1], [1, 0], 2)                      # in range: no error
+
+
+def _pair_dataset_fixture(g, tmp_path):
+    """Fake OGR / GDAL objects and the two pair-list folders the golden generator used (oracle/gen_golden.py)."""
+    from deepmerge_b200.MyUtils2 import DESIGNED_FIELDS
+    fields = list(g["fields"])
+    polys = FakeLayer([FakeFeature(r, {"PointID": fields[r]}) for r in range(len(fields))])
+
+    def point(i):
+        f = dict(zip(DESIGNED_FIELDS, g["attr"][i].tolist()))
+        f["inner"], f["object"] = int(g["inner"][i]), int(g["obj"][i])
+        return FakeFeature(i, f, (float(g["X"][i]), float(g["Y"][i])))
+
+    pts = FakeLayer([point(i) for i in range(len(g["X"]))])
+    pos, neg = tmp_path / "pos", tmp_path / "neg"
+    pos.mkdir()
+    neg.mkdir()
+    (pos / "tileA.txt").write_text("".join(f"{j},{a},{b},0,0\n" for j, (a, b) in enumerate(g["pos_pairs"])))
+    (neg / "tileB.txt").write_text("".join(f"{j},{a},{b},0,0\n" for j, (a, b) in enumerate(g["neg_pairs"])))
+
+    class DS:
+        def __init__(self, layer):
+            self.layer = layer
+
+        def GetLayer(self, i):
+            return self.layer
+
+    def open_vector(path):
+        layer = pts if path.endswith("PointsGCS.shp") else polys
+        return DS(layer), layer
+
+    def open_image(path):
+        return FakeRaster(g["arr"], geotransform=tuple(g["gt"]))
+
+    return str(pos), str(neg), open_vector, open_image
+
+
+def test_pair_dataset_class_builds_the_reference_item_list(golden_dir, tmp_path):
+    """MergingSegmensPairDataset(image_folder, polygon_folder, point_folder, positive_folder, negative_folder): same
+    attributes and, under the same seed, the item list of the executed reference (MyUtils1.py:20-38, :236-295)."""
+    g = np.load(os.path.join(golden_dir, "pair_dataset.npz"))
+    pos, neg, open_vector, open_image = _pair_dataset_fixture(g, tmp_path)
+    random.seed(int(g["seed"]))
+    ds = MyUtils1.MergingSegmensPairDataset("IF", "PF", "QF", pos, neg, open_vector=open_vector, open_image=open_image)
+    assert len(ds) == int(g["n"])
+    assert [ds.positive_number, ds.positive_pair_number, ds.negative_number, ds.negative_pair_number] == g["counts"].tolist()
+    assert [[d[0], str(d[1]), str(d[2]), str(d[3])] for d in ds.data] == g["data"].tolist()
+    assert set(ds.layers) == {"tileA", "tileB"} and set(ds.img_dataset) == {"tileA", "tileB"} and ds.band_num == 3
+    empty = MyUtils1.MergingSegmensPairDataset("IF", "PF", "QF", "", "", open_vector=open_vector, open_image=open_image)
+    assert len(empty) == 0 and empty.positive_pair_number == 0
