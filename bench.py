@@ -262,6 +262,10 @@ def b200_arm(args):
     peak, peak_kind = measured_peaks()
     achieved = alg_bytes / (rag_ms * 1e-3) / 1e9
     res = step()
+    # (a MergeResult holds views of the engine's buffers: keep what the line reports before the engine runs anything else)
+    root_l2 = res.root.clone()
+    n_roots = int((root_l2 == torch.arange(R, device=dev, dtype=torch.int32)).sum())
+    res_rounds, res_merges = res.rounds, res.merges
 
     # ---- end to end through the public API with HOST buffers -----------------------------------------
     # ScenePipeline: every step copies its inputs from pinned host memory and its label map back; the
@@ -333,12 +337,136 @@ def b200_arm(args):
     except Exception as ex:                              # never hide it: the record says what failed
         mlp_rec = {"error": repr(ex)}
 
+    # ---- the whole step with the pair-MLP as the scorer (R8 inside the merge loop) --------------------------------
+    # a hand-made "same object?" network: logit 0 = L1 distance of the two pooled embeddings (leaky-ReLU pairs), logit 1
+    # a constant -- it takes the same decisions as the L2 scorer on this scene, so the two steps do the same merges
+    mlp_step = None
+    try:
+        from deepmerge_b200 import PackedMLP
+        W1 = torch.zeros((2 * D, 2 * D))
+        i = torch.arange(D)
+        W1[i, i], W1[i, D + i], W1[D + i, i], W1[D + i, D + i] = 1.0, -1.0, -1.0, 1.0
+        W3 = torch.zeros((2, 2 * D))
+        W3[0] = 1.0
+        l1net = PackedMLP(W1.to(dev), torch.zeros(2 * D, device=dev), torch.eye(2 * D, device=dev),
+                          torch.zeros(2 * D, device=dev), W3.to(dev), torch.tensor([0.0, 4.0], device=dev))
+
+        def step_m():
+            return eng.run(sc.labels, sc.feats, 0.0, image=sc.image, xs=sc.xs, ys=sc.ys, mlp=l1net)
+
+        for _ in range(3):
+            rm = step_m()
+        km = max(3, args.steps // 3)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(km):
+            rm = step_m()
+        ev1.record()
+        torch.cuda.synchronize()
+        l1net.check()
+        mlp_step = {"scorer": "pair-MLP 200->200->200->2 (tcgen05), every live edge every round", "ms_per_step": ev0.elapsed_time(ev1) / km,
+                    "value": H * W / (ev0.elapsed_time(ev1) / km) / 1e3, "unit": "Mpx/s", "rounds": rm.rounds, "merges": rm.merges,
+                    "same_roots_as_l2": bool(torch.equal(rm.root, root_l2))}
+    except Exception as ex:
+        mlp_step = {"error": repr(ex)}
+
+    # ---- a multi-round workload: embeddings whose merges cascade over three rounds (deepmerge_b200.synth.cascade_feats) ---
+    multi = None
+    try:
+        from deepmerge_b200.synth import CASCADE_TAU, cascade_feats
+        cf = cascade_feats(sc, D)
+
+        def step_c(mr=64):
+            return eng.run(sc.labels, cf, CASCADE_TAU, image=sc.image, xs=sc.xs, ys=sc.ys, max_rounds=mr)
+
+        kc = max(3, args.steps // 3)
+        cum, edges_live = [], []
+        for mr in (0, 1, 2, 3, 64):
+            for _ in range(2):
+                rc = step_c(mr)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(kc):
+                rc = step_c(mr)
+            ev1.record()
+            torch.cuda.synchronize()
+            cum.append(ev0.elapsed_time(ev1) / kc)
+            edges_live.append(int(rc.edge_keys.shape[0]))
+        ms_c = cum[-1]
+        scored = sum(edges_live[:rc.rounds + 1])                    # E_0 (all edges) + the live edges after every round but the last
+        multi = {"workload": f"{H}x{W}, {R} segments, cascade embeddings (regions -> objects -> 4x4 groups -> 4x4 groups of groups), "
+                             f"tau {CASCADE_TAU}", "rounds": rc.rounds, "ms_per_step": ms_c, "value": H * W / ms_c / 1e3, "unit": "Mpx/s",
+                 "merges": rc.merges, "segments_after": int((rc.root == torch.arange(R, device=dev, dtype=torch.int32)).sum()),
+                 "live_edges_after_round_0_1_2_3": edges_live[:4], "ms_with_max_rounds_0_1_2_3": cum[:4],
+                 "ms_per_round_1_2_3": [cum[i + 1] - cum[i] for i in range(3)],
+                 "scored_edges": scored, "scored_edges_per_s": scored / (ms_c * 1e-3), "merged_edges_per_s": rc.merges / (ms_c * 1e-3)}
+    except Exception as ex:
+        multi = {"error": repr(ex)}
+
+    # ---- configs[3] micro-bench: adjacent-pair sampling + row gather + contrastive loss forward / backward at B = 960 -----
+    train = None
+    try:
+        import random
+        from deepmerge_b200 import MyUtils1
+        from deepmerge_b200.Losses import Loss
+        B = 960
+        lo_all, hi_all = rag.edge_keys >> 32, rag.edge_keys & 0xFFFFFFFF
+        npairs = min(100000, int(lo_all.shape[0]))
+        lo_h, hi_h = lo_all[:npairs].cpu().numpy(), hi_all[:npairs].cpu().numpy()
+        obj = sc.region_obj.cpu().numpy()
+        flags = (obj[lo_h] == obj[hi_h]).astype(np.int64)
+        off = np.zeros(R + 1, np.int64)
+        rop_h = sc.region_of_point.cpu().numpy()
+        order = np.argsort(np.where(rop_h >= 0, rop_h, R), kind="stable")
+        np.cumsum(np.bincount(rop_h[rop_h >= 0], minlength=R), out=off[1:])
+        fields = {}
+
+        class Fields:                               # PointID strings of the polygons, built when a pair asks for them
+            def __getitem__(self, r):
+                f = fields.get(r)
+                if f is None:
+                    f = fields[r] = " ".join(str(int(v)) for v in order[off[r]:off[r + 1]]) or "0"
+                return f
+
+        crit = Loss(1.0, 0.1, 0)
+        random.seed(1)
+        sel = np.random.default_rng(1).integers(0, npairs, size=(8, B))
+
+        def train_step(k):
+            pairs = [(int(lo_h[j]), int(hi_h[j])) for j in sel[k % 8]]
+            left, right, _ = MyUtils1.pairs_to_arrays(MyUtils1.sample_pairs(Fields(), pairs, 0))
+            flag = flags[sel[k % 8]]
+            li, ri = torch.from_numpy(left).to(dev, non_blocking=True), torch.from_numpy(right).to(dev, non_blocking=True)
+            a_rows = torch.empty((B, D), dtype=torch.float32, device=dev)
+            b_rows = torch.empty((B, D), dtype=torch.float32, device=dev)
+            L.check(L.dm_gather_rows(_p(sc.feats), D, _p(li), B, _p(a_rows), s), "dm_gather_rows")
+            L.check(L.dm_gather_rows(_p(sc.feats), D, _p(ri), B, _p(b_rows), s), "dm_gather_rows")
+            a_rows.requires_grad_(True)
+            loss = crit(a_rows, b_rows, torch.from_numpy(flag).to(dev, non_blocking=True))
+            loss.backward()
+            return loss
+
+        for k in range(3):
+            train_step(k)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        kt = max(8, args.steps)
+        for k in range(kt):
+            lossv = train_step(k)
+        torch.cuda.synchronize()
+        tms = (time.perf_counter() - t0) * 1e3 / kt
+        train = {"workload": "configs[3] micro-bench: per step 960 labelled adjacent pairs -> one random member point per side "
+                             "(random.randint, as MyUtils1.py:278-279) -> dm_gather_rows x 2 -> Loss forward + backward",
+                 "batch": B, "ms_per_step": tms, "pairs_per_s": B / (tms * 1e-3), "loss": float(lossv.item()),
+                 "note": "host-bound: the reference's per-pair Python sampling dominates (the three kernels take ~20 us)"}
+    except Exception as ex:
+        train = {"error": repr(ex)}
+
     # ---- CPU baseline: the oracle port on a bounded sample, same box, all host cores ---------------------------
     cpu = None
     if not args.no_cpu:
         cpu, _, _ = cpu_baseline_record(cfg, min(args.cpu_side, H))
 
-    n_roots = int((res.root == torch.arange(R, device=dev, dtype=torch.int32)).sum())
     line = {
         "metric": "megapixels/sec end-to-end (RAG+pool+score+merge+relabel)", "value": mpx, "unit": "Mpx/s",
         "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
@@ -346,8 +474,8 @@ def b200_arm(args):
         "config": {"workload": WORKLOAD if not args.side else f"{H}x{W} reduced scene", "H": H, "W": W, "bands": C,
                    "segments": R, "edges": E0, "points": N, "embed_dim": D, "tau": cfg["tau"],
                    "l2_policy": "inputs (labels+image 800 MB) larger than L2, no flush needed"},
-        "merged_edges_per_s": res.merges / (ms * 1e-3), "scored_edges_per_s": E0 / (ms * 1e-3),
-        "segments_after": n_roots, "rounds": res.rounds,
+        "merged_edges_per_s": res_merges / (ms * 1e-3), "scored_edges_per_s": E0 / (ms * 1e-3),
+        "segments_after": n_roots, "rounds": res_rounds,
         "e2e": {"value": H * W / e2e_ms / 1e3, "unit": "Mpx/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "api": "ScenePipeline.run (H2D / compute / D2H of neighbouring steps overlap)",
                 "unpipelined_ms_per_step": e2e_single_ms, "unpipelined_value": H * W / e2e_single_ms / 1e3},
@@ -356,7 +484,8 @@ def b200_arm(args):
                      "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                      "frac_of_nominal_8TBs": achieved / 8000.0, "ms": rag_ms, "algorithmic_bytes": alg_bytes,
                      "traffic": ncu_traffic("rag_pool_kernel") if not args.side else None},
-        "mlp": mlp_rec, "cpu_baseline": cpu, "clocks": clocks.summary(),
+        "mlp": mlp_rec, "mlp_step": mlp_step, "multi_round": multi, "train_pairs": train, "cpu_baseline": cpu,
+        "clocks": clocks.summary(),
     }
     print(json.dumps(line), flush=True)
 

@@ -57,3 +57,34 @@ def synth_scene(H, W, R, C=4, P=4, D=100, seed=1234, device=None, rows=None, wit
             feats = torch.empty((nreg * P, D), dtype=torch.float32, device=dev)
             L.check(L.dm_synth_feats(_p(feats), _p(rop), _p(robj), None, nreg * P, D, seed, s), "dm_synth_feats")
     return Scene(labels, image, xs, ys, rop, feats, robj, nreg, H, W)
+
+
+CASCADE_TAU = 0.5
+CASCADE_AMPL = (0.25, 0.27386127, 0.27386127, 8.0)
+
+
+def cascade_feats(scene: Scene, D=100):
+    """Embeddings of the multi-round workload (bench.py `multi_round`; the same construction as the oracle's
+    synth_cascade_feats, bit for bit): four one-hot parts per point -- region, object, group of 4 x 4 objects, top --
+    whose amplitudes make regions merge into objects in round 1, objects into groups in round 2 (the merged means have
+    lost most of the region part), groups into tops in round 3, with tau = CASCADE_TAU."""
+    if D < 100:
+        raise ValueError("the cascade construction uses 100 embedding dimensions")
+    dev = scene.labels.device
+    g = grid_pitch(scene.H, scene.W, scene.n_regions)
+    ncx, ncx_o = -(-scene.W // g), -(-scene.W // (4 * g))
+    rop = scene.region_of_point.to(torch.int64)
+    ok = rop >= 0
+    r = torch.where(ok, rop, torch.zeros_like(rop))
+    cx, cy = r % ncx, r // ncx
+    o = scene.region_obj.to(torch.int64)[r]
+    ox, oy = o % ncx_o, o // ncx_o
+    sx, sy = ox // 4, oy // 4
+    tx, ty = sx // 4, sy // 4
+    idx = [(cx % 8) + 8 * (cy % 5), 40 + (ox % 6) + 6 * (oy % 5), 70 + (sx % 5) + 5 * (sy % 4), 90 + (tx % 5) + 5 * (ty % 2)]
+    f = torch.zeros((rop.shape[0], D), dtype=torch.float32, device=dev)
+    rows = torch.arange(rop.shape[0], device=dev)
+    for k, a in zip(idx, CASCADE_AMPL):
+        f[rows, k] = a
+    f[~ok] = 0
+    return f

@@ -155,6 +155,41 @@ def synth_feats(point_obj, D=100, seed=1234):
     return ((ci * 128 + ni).astype(np.float32) * np.float32(1.0 / 2097152.0)).astype(np.float32)
 
 
+# cascade scene: embeddings whose merges need THREE rounds (regions -> objects -> groups of objects -> groups of groups)
+CASCADE_TAU = 0.5
+CASCADE_AMPL = (0.25, 0.27386127, 0.27386127, 8.0)      # region / object / group / top part; 2 a^2 = 0.5, 0.6, 0.6 tau^2
+
+
+def synth_cascade_feats(region_of_point, region_obj, H, W, R, D=100):
+    """fp32 [N, D] embeddings for the multi-round workload (spec of this build; SURVEY.md 8(d)(ii) asks for scored
+    edges over several rounds).  A point of region r (grid cell (cx, cy), object o = region_obj[r] with object-grid
+    cell (ox, oy), group = 4 x 4 objects, top = 4 x 4 groups) gets the sum of four one-hot parts in disjoint
+    dimension ranges: region part a0 e[k], object part a1 e[40 + j], group part a2 e[70 + m], top part a3 e[90 + t],
+    the indices taken modulo small windows so that ADJACENT cells never share one.  With tau = 0.5: two regions of
+    one object are at distance 0.707 tau (merge in round 1), regions of different objects at >= 1.05 tau; merged
+    objects of one group are at ~0.8 tau (round 2), of different groups at >= 1.1 tau; merged groups of one top
+    at ~0.8 tau (round 3); tops never merge."""
+    assert D >= 100
+    g = grid_pitch(H, W, R)
+    ncx = -(-W // g)
+    ncx_o = -(-W // (4 * g))
+    rop = np.asarray(region_of_point, np.int64)
+    ok = rop >= 0
+    r = np.where(ok, rop, 0)
+    cx, cy = r % ncx, r // ncx
+    o = np.asarray(region_obj, np.int64)[r]
+    ox, oy = o % ncx_o, o // ncx_o
+    sx, sy = ox // 4, oy // 4
+    tx, ty = sx // 4, sy // 4
+    idx = [(cx % 8) + 8 * (cy % 5), 40 + (ox % 6) + 6 * (oy % 5), 70 + (sx % 5) + 5 * (sy % 4), 90 + (tx % 5) + 5 * (ty % 2)]
+    f = np.zeros((rop.shape[0], D), np.float32)
+    rows = np.arange(rop.shape[0])
+    for k, a in zip(idx, CASCADE_AMPL):
+        f[rows, k] = np.float32(a)
+    f[~ok] = 0
+    return f
+
+
 def synth_scene(H, W, R, C=4, P=4, D=100, seed=1234):
     labels, nreg = synth_labels(H, W, R, seed)
     region_obj, nobj = synth_region_objects(H, W, R, seed)

@@ -411,6 +411,31 @@ def test_regions_without_sample_points_never_merge(cuda):
     assert np.array_equal(got.root.cpu().numpy(), want["root"])
 
 
+def test_cascade_scene_needs_three_rounds_and_equals_the_oracle(cuda):
+    """The multi-round workload of bench.py: the device generator equals the oracle's, the merge takes exactly three
+    rounds (regions -> objects -> groups -> tops), and roots / label map / merged statistics equal the oracle's after
+    every round limit."""
+    from deepmerge_b200 import merge_scene
+    from deepmerge_b200.synth import CASCADE_TAU, cascade_feats, synth_scene
+    H, W, R = 600, 800, 4000
+    sc = o.synth_scene(H, W, R, C=4)
+    d = synth_scene(H, W, R, C=4, device=cuda)
+    f = o.synth_cascade_feats(sc["region_of_point"], sc["region_obj"], H, W, R)
+    fd = cascade_feats(d)
+    assert np.array_equal(fd.cpu().numpy(), f)
+    n = sc["n_regions"]
+    for mr in (1, 2, 64):
+        want = o.merge_scene(sc["labels"], n, sc["region_of_point"], f, tau=CASCADE_TAU, max_rounds=mr)
+        got = merge_scene(d.labels, fd, CASCADE_TAU, n_regions=n, image=d.image, xs=d.xs, ys=d.ys, max_rounds=mr)
+        assert got.rounds == want["rounds"] == min(mr, 3) and got.merges == want["merges"]
+        assert np.array_equal(got.root.cpu().numpy(), want["root"])
+        assert np.array_equal(got.labels.cpu().numpy(), want["labels"])
+        roots = np.unique(want["root"])
+        assert np.array_equal(got.area.cpu().numpy()[roots], want["area"][roots])
+        assert np.array_equal(got.perimeter.cpu().numpy()[roots], want["perim"][roots])
+        assert np.array_equal(keys_np(got.edge_keys), want["keys"])
+
+
 def test_merge_graph_max_rounds_and_snake(cuda):
     from deepmerge_b200 import merge_graph
     R, D = 5000, 8
