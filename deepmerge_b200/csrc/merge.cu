@@ -64,6 +64,51 @@ __global__ void uf_union_kernel(int32_t* __restrict__ parent, const uint64_t* __
     }
 }
 
+__device__ __forceinline__ void uf_unite(int32_t* parent, int a, int b) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    while (a != b) {
+        if (a > b) { int t = a; a = b; b = t; }
+        const int old = atomicCAS(&parent[b], b, a);
+        if (old == b) break;
+        b = uf_find(parent, old);
+        a = uf_find(parent, a);
+    }
+}
+
+// Distributed union-find, frontier exchange.  A component can span two row tiles only through a region both ranks see,
+// so after the local unions every rank publishes, for each alive component it shares with another rank, the pair
+// (component, its local root); every rank then unites ALL ranks' pairs into its own forest.  The pairs carry the whole
+// cross-rank connectivity (a local root is the minimum id of its local component, and the global minimum is the minimum
+// of the local roots), so no iteration and no convergence test are needed.
+__global__ void shard_frontier_pairs_kernel(const int32_t* __restrict__ parent, const uint8_t* __restrict__ alive,
+                                            const int32_t* __restrict__ mask, int my_bit, int64_t R,
+                                            uint64_t* __restrict__ pairs, int64_t cap, unsigned long long* __restrict__ n_out) {
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < R; x += (int64_t)gridDim.x * blockDim.x) {
+        if (!alive[x]) continue;
+        const int m = mask[x];
+        if (!(m & my_bit) || !(m & ~my_bit)) continue;             // not seen here, or seen here only
+        const int r = parent[x];
+        if (r == (int)x) continue;
+        const unsigned long long i = atomicAdd(n_out, 1ull);
+        if ((long long)i < cap) pairs[i] = ((uint64_t)(unsigned)x << 32) | (unsigned)r;
+    }
+}
+__global__ void uf_union_slots_kernel(int32_t* __restrict__ parent, const unsigned char* __restrict__ slots, int n_slots,
+                                      int64_t slot_bytes, int64_t cap, int64_t R) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)n_slots * cap;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int slot = (int)(i / cap);
+        const int64_t j = i - (int64_t)slot * cap;
+        const unsigned char* sb = slots + (size_t)slot * slot_bytes;
+        const long long n = *(const long long*)sb;
+        if (j >= n || j >= cap) continue;
+        const uint64_t k = ((const uint64_t*)(sb + 80))[j];
+        const int a = key_lo(k), b = key_hi(k);
+        if ((unsigned)a < (unsigned)R && (unsigned)b < (unsigned)R) uf_unite(parent, a, b);
+    }
+}
+
 __global__ void uf_compress_kernel(int32_t* __restrict__ parent, int64_t n) {
     for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (int64_t)gridDim.x * blockDim.x) {
         // roots never change here, so racing writes of final roots are benign
@@ -371,6 +416,54 @@ __global__ void shard_frontier_kernel(const int32_t* __restrict__ mask_cnt, cons
         send[r] = ((m & (m - 1)) != 0 && cnt_local[r] > 0) ? 1 : 0;   // seen by two ranks, and this one has points of it
     }
 }
+// Fused "all-gather" of fixed-layout slots over NVLink peer memory: this rank's slot -- a header and up to two segments
+// whose used length is the header's leading count -- is stored straight into slot `rank` of EVERY rank's gathered buffer
+// (peer_bases[p] = base address of rank p's buffer, mapped into this process; p == rank is the local copy).  Only the
+// used part travels.  A barrier over all ranks (signal pads) after this kernel makes the stores visible.
+__global__ void __launch_bounds__(256) peer_put_kernel(const unsigned char* __restrict__ src, const long long* __restrict__ peer_bases,
+                                                       int world, int rank, int64_t slot_bytes, int64_t hdr_units,
+                                                       int64_t seg0_off, int64_t seg0_elem, int64_t seg1_off, int64_t seg1_elem,
+                                                       int64_t cap) {
+    const long long n = imin64(*(const long long*)src, cap);
+    const int64_t u0 = (n * seg0_elem + 15) >> 4, u1 = (n * seg1_elem + 15) >> 4;
+    const int64_t total = hdr_units + u0 + u1;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
+        int64_t off;
+        if (u < hdr_units) off = u << 4;
+        else if (u < hdr_units + u0) off = seg0_off + ((u - hdr_units) << 4);
+        else off = seg1_off + ((u - hdr_units - u0) << 4);
+        const uint4 v = *(const uint4*)(src + off);
+        for (int p = 0; p < world; ++p)
+            *(uint4*)((unsigned char*)peer_bases[p] + (size_t)rank * slot_bytes + off) = v;
+    }
+}
+
+// The flag words of one round of the distributed loop, filled from the engine's counters in ONE launch (they were a
+// dozen elementwise launches from the host): flags[0] = edges selected; first round: [3] tile edge-list overflow, [4] bad
+// label, [5] internal error, [6] raw entries needed; then flags -> the header of the frontier slot.
+__global__ void shard_round_flags_kernel(const int64_t* __restrict__ counts, int64_t* __restrict__ flags, int first_round,
+                                         int64_t* __restrict__ slot_flags) {
+    const int i = threadIdx.x;
+    if (i >= 8) return;
+    int64_t v = flags[i];
+    if (i == 0) v = counts[4];
+    if (first_round) {
+        if (i == 3) v = counts[2] != 0;
+        if (i == 4) v = counts[3] == 1;
+        if (i == 5) v = counts[3] > 1;
+        if (i == 6) v = counts[1];
+    }
+    flags[i] = v;
+    slot_flags[i] = v;
+}
+// flag = max(flag, any slot's entry count > capacity)
+__global__ void slots_overflow_kernel(const unsigned char* __restrict__ slots, int n_slots, int64_t slot_bytes, int64_t cap,
+                                      int64_t* __restrict__ flag) {
+    bool over = false;
+    for (int g = threadIdx.x; g < n_slots; g += blockDim.x) over |= *(const int64_t*)(slots + (size_t)g * slot_bytes) > cap;
+    if (over) *flag = 1;
+}
+
 __global__ void any_diff_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int64_t n,
                                 int64_t* __restrict__ flag) {
     bool d = false;
@@ -401,6 +494,65 @@ extern "C" int dm_shard_frontier(const int32_t* mask_cnt, const int32_t* cnt_loc
     if (n_regions == 0) return DM_OK;
     if (!mask_cnt || !cnt_local || !cnt || !send) return DM_ERR_BAD_ARG;
     DM_COUNT_LAUNCH(); merge::shard_frontier_kernel<<<grid_for(n_regions), 256, 0, S(stream)>>>(mask_cnt, cnt_local, n_regions, cnt, send);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_shard_frontier_pairs(const int32_t* parent, const uint8_t* alive, const int32_t* mask, int rank,
+                                       int64_t n_regions, void* slot, int64_t capacity, dm_stream_t stream) {
+    if (n_regions < 0 || capacity < 0 || rank < 0 || rank > 30 || !slot || ((uintptr_t)slot & 15)) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    DM_CUDA(cudaMemsetAsync(slot, 0, 16, s));                       // count; the caller owns the 8 flag words behind it
+    if (n_regions == 0) return DM_OK;
+    if (!parent || !alive || !mask) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::shard_frontier_pairs_kernel<<<grid_for(n_regions), 256, 0, s>>>(
+        parent, alive, mask, 1 << rank, n_regions, (uint64_t*)((unsigned char*)slot + 80), capacity, (unsigned long long*)slot);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_uf_union_slots(int32_t* parent, const void* slots, int64_t n_slots, int64_t slot_bytes, int64_t capacity,
+                                 int64_t n_regions, dm_stream_t stream) {
+    if (n_slots < 0 || capacity < 0 || n_regions < 0 || slot_bytes < 80 + 8 * capacity || (slot_bytes & 15)) return DM_ERR_BAD_ARG;
+    if (n_slots == 0 || capacity == 0 || n_regions == 0) return DM_OK;
+    if (!parent || !slots) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::uf_union_slots_kernel<<<grid_for(n_slots * capacity), 256, 0, S(stream)>>>(
+        parent, (const unsigned char*)slots, (int)n_slots, slot_bytes, capacity, n_regions);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_peer_put_slot(const void* slot, const int64_t* peer_bases_dev, int64_t world, int64_t rank, int64_t slot_bytes,
+                                int64_t header_bytes, int64_t seg0_offset, int64_t seg0_elem_bytes, int64_t seg1_offset,
+                                int64_t seg1_elem_bytes, int64_t capacity, dm_stream_t stream) {
+    if (world < 1 || world > 31 || rank < 0 || rank >= world || capacity < 0 || header_bytes < 16 || (header_bytes & 15) ||
+        (slot_bytes & 15) || (seg0_offset & 15) || (seg1_offset & 15) || seg0_elem_bytes < 0 || seg1_elem_bytes < 0 ||
+        seg0_offset + capacity * seg0_elem_bytes > slot_bytes || seg1_offset + capacity * seg1_elem_bytes > slot_bytes)
+        return DM_ERR_BAD_ARG;
+    if (!slot || !peer_bases_dev || ((uintptr_t)slot & 15)) return DM_ERR_BAD_ARG;
+    const int64_t units = header_bytes / 16 + (capacity * seg0_elem_bytes + 15) / 16 + (capacity * seg1_elem_bytes + 15) / 16;
+    DM_COUNT_LAUNCH(); merge::peer_put_kernel<<<grid_for(units), 256, 0, S(stream)>>>(
+        (const unsigned char*)slot, (const long long*)peer_bases_dev, (int)world, (int)rank, slot_bytes, header_bytes / 16, seg0_offset,
+        seg0_elem_bytes, seg1_offset, seg1_elem_bytes, capacity);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_shard_round_flags(const int64_t* counts, int64_t* flags, int first_round, int64_t* slot_flags,
+                                    dm_stream_t stream) {
+    if (!counts || !flags || !slot_flags) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::shard_round_flags_kernel<<<1, 32, 0, S(stream)>>>(counts, flags, first_round, slot_flags);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_slots_overflow(const void* slots, int64_t n_slots, int64_t slot_bytes, int64_t capacity, int64_t* flag_dev,
+                                 dm_stream_t stream) {
+    if (n_slots < 0 || n_slots > 4096 || slot_bytes < 16 || capacity < 0 || !flag_dev) return DM_ERR_BAD_ARG;
+    if (n_slots == 0) return DM_OK;
+    if (!slots) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::slots_overflow_kernel<<<1, 64, 0, S(stream)>>>((const unsigned char*)slots, (int)n_slots, slot_bytes, capacity,
+                                                                       flag_dev);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

@@ -85,6 +85,52 @@ def all_gather_slots(t: torch.Tensor, dist, group=None):
     return out
 
 
+class PeerSlots:
+    """Gathered slot buffers [world x slot_bytes] in torch symmetric memory: every rank's buffer is mapped into every
+    process, so an exchange is ONE kernel of this library storing the rank's slot into all peers over NVLink
+    (dm_peer_put_slot) plus a signal-pad barrier -- no collective call.  Two buffers alternate: a buffer is rewritten
+    only after every rank has passed the barrier that follows its last read."""
+
+    def __init__(self, dist, group, slot_bytes, device):
+        import torch.distributed._symmetric_memory as symm
+        world = dist.get_world_size(group)
+        name = (group if group is not None else dist.group.WORLD).group_name
+        self.slot_bytes, self.world = slot_bytes, world
+        self.bufs = []
+        for _ in range(2):
+            t = symm.empty(world * slot_bytes, dtype=torch.uint8, device=device)
+            h = symm.rendezvous(t, name)
+            bases = torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64, device=device)
+            t.zero_()
+            self.bufs.append((t, h, bases))
+        torch.cuda.synchronize(device)
+        self.bufs[0][1].barrier()
+        self.k = 0
+
+    def exchange(self, L, slot, rank, header_bytes, seg0, seg1, capacity, stream):
+        """slot -> every rank's gathered buffer; returns this rank's gathered view [world, slot_bytes]."""
+        from .raster import _p
+        t, h, bases = self.bufs[self.k]
+        self.k ^= 1
+        L.check(L.dm_peer_put_slot(_p(slot), _p(bases), self.world, rank, self.slot_bytes, header_bytes, seg0[0], seg0[1],
+                                   seg1[0], seg1[1], capacity, stream), "dm_peer_put_slot")
+        h.barrier()
+        return t.view(self.world, self.slot_bytes)
+
+
+def _peer_exchange_possible(dist):
+    """Symmetric memory needs the real torch.distributed over NCCL (one process per GPU); DM_SHARD_PEER=0 forces the
+    collective path."""
+    import os
+    if os.environ.get("DM_SHARD_PEER", "1") == "0":
+        return False
+    try:
+        import torch.distributed as td
+        return dist is td and td.is_initialized() and td.get_backend() == "nccl"
+    except Exception:
+        return False
+
+
 class ShardedMergeEngine:
     """One rank's share of a scene sharded by rows.  Wraps a MergeEngine sized for the tile.
 
@@ -125,6 +171,7 @@ class ShardedMergeEngine:
         dev, R, D = e.dev, e.R, e.D
         # frontier / cross-component rows per rank and exchange (overflow is detected and reported)
         self.row_cap = int(self.row_capacity) if self.row_capacity else int(min(R, max(4096, self.W // 2)))
+        self.row_cap += (-self.row_cap) % 4                        # 16-byte aligned segments inside the slots
         z = lambda *sh, dt: torch.zeros(*sh, dtype=dt, device=dev)
         self.seen, self.grew, self.send, self.seen_comp = (z(R, dt=torch.uint8) for _ in range(4))
         self.mask_old = z(R, dt=torch.int32)
@@ -142,7 +189,23 @@ class ShardedMergeEngine:
         # [0] selected, [1] parent changed, [2] row-slot overflow, [3] tile edge-list overflow, [4] bad label, [5] internal
         # error, [6] raw entries needed -- [0] and [2:7] are all-reduced with MAX once per round, so that every rank raises
         # (or goes on) together: a rank that left the loop alone would leave its peers hanging in the next collective
+        # frontier pairs of the distributed union-find: [count | pad | pairs] per rank, one all_gather per round
+        # [count | pad | 8 flag words | pairs]: the round's flags travel with the pairs
+        self.fslot_bytes = 80 + 8 * self.row_cap
+        self.fslot_bytes += (-self.fslot_bytes) % 16
+        self.fslot = z(self.fslot_bytes, dt=torch.uint8)
+        self.fslot_flags = self.fslot[16:80].view(torch.int64)
         self.flags = z(8, dt=torch.int64)
+        self.peer_rows = self.peer_pairs = None
+        if _peer_exchange_possible(self.dist):
+            try:
+                self.peer_rows = PeerSlots(self.dist, self.group, self.slot_bytes, dev)
+                self.peer_pairs = PeerSlots(self.dist, self.group, self.fslot_bytes, dev)
+            except Exception as ex:                                # no NVLink peer access / symmetric memory on this box
+                self.peer_rows = self.peer_pairs = None
+                self.peer_error = repr(ex)
+        self.host_fflags = torch.zeros((self.world, 10), dtype=torch.int64).pin_memory()
+        self.hdr_dev = z(self.world, 80, dt=torch.uint8)
         self.host_flags = torch.zeros(8, dtype=torch.int64).pin_memory()
 
     def _exchange_rows(self, flag, add):
@@ -152,11 +215,13 @@ class ShardedMergeEngine:
         e, L, dist, s = self.eng, self.eng.L, self.dist, _stream()
         L.check(L.dm_rows_pack(_p(flag), _p(e.sum), e.R, e.D, _p(self.slot_ids), _p(self.slot_rows), self.row_cap,
                                _p(self.slot_n), s), "dm_rows_pack")
-        g = all_gather_slots(self.slot, dist, self.group).view(self.world, self.slot_bytes)
         rc = self.row_cap
+        if self.peer_rows is not None:     # one kernel storing the used part of the slot into every peer + a barrier
+            g = self.peer_rows.exchange(L, self.slot, self.rank, 16, (16, 4), (16 + 4 * rc, 4 * e.D), rc, s)
+        else:
+            g = all_gather_slots(self.slot, dist, self.group).view(self.world, self.slot_bytes)
         # a slot that overflowed on ANY rank is seen by every rank in the gathered counts: all of them flag it
-        over = (g[:, :8].contiguous().view(torch.int64) > rc).any().to(torch.int64).reshape(1)
-        self.flags[2:3].copy_(torch.maximum(self.flags[2:3], over))
+        L.check(L.dm_slots_overflow(_p(g), self.world, self.slot_bytes, rc, self.flags[2:3].data_ptr(), s), "dm_slots_overflow")
         g_n = [g[r, :8].view(torch.int64) for r in range(self.world)]
         g_ids = [g[r, 16:16 + 4 * rc].view(torch.int32) for r in range(self.world)]
         g_rows = [g[r, 16 + 4 * rc:16 + 4 * rc * (e.D + 1)].view(torch.float32) for r in range(self.world)]
@@ -168,13 +233,16 @@ class ShardedMergeEngine:
         else:         # whole rows from their single sender: one launch for all slots
             L.check(L.dm_rows_unpack_slots(_p(g), self.world, self.slot_bytes, rc, e.R, e.D, _p(e.sum), 0, s), "dm_rows_unpack_slots")
 
-    def _read_flags(self):
+    def _read_headers(self, gathered):
+        """The round's one host read-back: the slot headers of all ranks ([count, pad, 8 flags] each) and this rank's
+        engine counters."""
         e = self.eng
-        self.host_flags.copy_(self.flags, non_blocking=True)
+        self.hdr_dev.copy_(gathered[:, :80])                       # one strided copy of the headers, then one to the host
+        self.host_fflags.copy_(self.hdr_dev.view(torch.int64).view(self.world, 10), non_blocking=True)
         e.host_counts.copy_(e.counts, non_blocking=True)
         e.done.record()
         e.done.synchronize()
-        return self.host_flags.tolist(), e.host_counts.tolist()
+        return self.host_fflags.tolist(), e.host_counts.tolist()
 
     def run(self, labels_tile, feats_local, tau, *, image_tile=None, xs_local=None, ys_local_rel=None, max_rounds=64,
             gather_outputs=True):
@@ -223,38 +291,40 @@ class ShardedMergeEngine:
             while True:
                 L.check(L.dm_merge_select_l2(_p(e.scores), float(tau), _p(n_edges), cap, _p(e.selected),
                                              e.counts[4:5].data_ptr(), s), "dm_merge_select_l2")
-                self.flags[0:1].copy_(e.counts[4:5])
-                if rounds == 0:                                     # this rank's tile-pass conditions travel with the count
-                    self.flags[3:4].copy_((e.counts[2:3] != 0).to(torch.int64))
-                    self.flags[4:5].copy_((e.counts[3:4] == 1).to(torch.int64))
-                    self.flags[5:6].copy_((e.counts[3:4] > 1).to(torch.int64))
-                    self.flags[6:7].copy_(e.counts[1:2])
-                dist.all_reduce(self.flags, op=MAX, group=grp)      # one collective: "any rank selected" + every error flag
-                f, c = self._read_flags()
+                # Union-find of the round, prepared BEFORE anyone knows whether the round takes place: local unions, then the
+                # frontier pairs (shared component, its local root).  The pairs of all ranks carry the whole cross-tile
+                # connectivity -- no iteration, no convergence test -- and the round's flags ("edges selected", errors)
+                # travel in the same slot: ONE exchange per round.  (Nothing selected anywhere: no unions, no pairs.)
+                if rounds < max_rounds:
+                    L.check(L.dm_uf_union(_p(e.parent), _p(e.keys), _p(e.selected), _p(n_edges), cap, s), "dm_uf_union")
+                    L.check(L.dm_uf_compress(_p(e.parent), R, s), "dm_uf_compress")
+                    L.check(L.dm_shard_frontier_pairs(_p(e.parent), _p(e.alive), _p(self.mask), self.rank, R, _p(self.fslot),
+                                                      self.row_cap, s), "dm_shard_frontier_pairs")
+                else:
+                    self.fslot[:16].zero_()
+                # the round's flags (edges selected; first round: this rank's tile-pass conditions) -> the slot header
+                L.check(L.dm_shard_round_flags(_p(e.counts), _p(self.flags), int(rounds == 0), _p(self.fslot_flags), s),
+                        "dm_shard_round_flags")
+                if self.peer_pairs is not None:                     # one kernel of NVLink peer stores + a barrier
+                    fg = self.peer_pairs.exchange(L, self.fslot, self.rank, 80, (80, 8), (80, 0), self.row_cap, s)
+                else:
+                    fg = all_gather_slots(self.fslot, dist, grp).view(self.world, self.fslot_bytes)
+                hf, c = self._read_headers(fg)
+                f = [max(int(h[2 + k]) for h in hf) for k in range(8)]     # every rank sees every rank's flags: all act alike
                 if f[4] != 0:
                     raise ValueError("labels contain ids >= n_regions")
                 if f[5] != 0 or f[3] != 0:
                     raise RuntimeError("tile edge list overflow / pipeline error (capacity %d, needed %d)" % (cap, f[6]))
-                if f[2] != 0:
+                if f[2] != 0 or any(int(h[0]) > self.row_cap for h in hf):
                     raise RuntimeError("row exchange slot overflow (row_cap %d)" % self.row_cap)
                 merges += int(c[5])
                 if f[0] == 0 or rounds == max_rounds:
                     break
                 rounds += 1
-                # union-find: local unions, then all_reduce(min) + re-union until every rank holds the same forest
-                L.check(L.dm_uf_union(_p(e.parent), _p(e.keys), _p(e.selected), _p(n_edges), cap, s), "dm_uf_union")
+                L.check(L.dm_uf_union_slots(_p(e.parent), _p(fg), self.world, self.fslot_bytes, self.row_cap, R, s),
+                        "dm_uf_union_slots")
                 L.check(L.dm_uf_compress(_p(e.parent), R, s), "dm_uf_compress")
-                while True:
-                    # two merge iterations per convergence check (one host round trip instead of two in the usual case)
-                    for _ in range(2):
-                        dist.all_reduce(e.parent, op=MIN, group=grp)
-                        self.agreed.copy_(e.parent)
-                        L.check(L.dm_uf_union(_p(e.parent), _p(e.keys), _p(e.selected), _p(n_edges), cap, s), "dm_uf_union")
-                        L.check(L.dm_uf_compress(_p(e.parent), R, s), "dm_uf_compress")
-                    L.check(L.dm_any_diff_i32(_p(e.parent), _p(self.agreed), R, self.flags[1:2].data_ptr(), s), "dm_any_diff_i32")
-                    dist.all_reduce(self.flags[1:2], op=MAX, group=grp)
-                    if int(self.flags[1].item()) == 0:
-                        break
+                dist.all_reduce(e.parent, op=MIN, group=grp)       # fills in the regions this rank does not see
                 # rows of components that grew across a tile border go to every rank that now sees them
                 self.mask_old.copy_(self.mask)
                 L.check(L.dm_shard_propagate(_p(e.parent), _p(e.alive), _p(self.mask), _p(self.grew), R, s), "dm_shard_propagate")

@@ -295,6 +295,36 @@ int dm_shard_seen(const int64_t* area, uint8_t* seen, const int32_t* cnt, int ra
 int dm_shard_frontier(const int32_t* mask_cnt, const int32_t* cnt_local, int64_t n_regions, int32_t* cnt, uint8_t* send,
                       dm_stream_t stream);
 int dm_any_diff_i32(const int32_t* a, const int32_t* b, int64_t n, int64_t* flag_dev, dm_stream_t stream);
+/* Distributed union-find by FRONTIER EXCHANGE (one all-gather of a few hundred pairs per round, no iteration): a component
+ * can span two row tiles only through a region both ranks see.  After its local unions (dm_uf_union + dm_uf_compress) a
+ * rank writes, for every alive component x it shares with another rank (mask[x] has its bit and another one) and whose
+ * local root differs from x, the pair (x << 32 | root) into a slot [int64 count | int64 pad | int64 flags[8] | u64
+ * pairs[capacity]] (dm_shard_frontier_pairs; count > capacity = overflow, nothing is written beyond capacity; the eight
+ * flag words are the caller's: the round's "edges selected" count and error flags travel with the pairs).  The slots of all ranks are
+ * all-gathered and dm_uf_union_slots unites every pair of every slot into the rank's own forest; after dm_uf_compress the
+ * regions a rank sees point at their GLOBAL root (the minimum id of the component: a local root is the minimum of its
+ * local component and it is part of a pair).  One all_reduce(MIN) of parent then fills in the regions a rank does not see. */
+int dm_shard_frontier_pairs(const int32_t* parent, const uint8_t* alive, const int32_t* mask, int rank, int64_t n_regions,
+                            void* slot, int64_t capacity, dm_stream_t stream);
+int dm_uf_union_slots(int32_t* parent, const void* slots, int64_t n_slots, int64_t slot_bytes, int64_t capacity,
+                      int64_t n_regions, dm_stream_t stream);
+/* The exchange step of the sharded path as ONE kernel over NVLink peer memory instead of a collective call: the slot of
+ * this rank -- a header (header_bytes, its first int64 the entry count) and up to two segments holding count entries of
+ * segK_elem_bytes each at segK_offset -- is stored into slot `rank` of every rank's gathered buffer [world x slot_bytes];
+ * peer_bases_dev[p] is the device address of rank p's buffer as mapped into this process (CUDA IPC / symmetric memory;
+ * the caller's communicator stays opaque to the library).  Only the used part travels.  The caller runs a barrier over
+ * the ranks after it (and alternates two buffers, so that a buffer is rewritten only after every rank has passed the
+ * barrier that follows its last read).  All offsets / sizes in bytes, multiples of 16 where they are addresses. */
+/* host-side glue of the distributed loop as single launches: dm_shard_round_flags fills the eight flag words of a round
+ * from the engine's counters (flags[0] = counts[4] edges selected; first round also [3] = counts[2] != 0 overflow, [4] =
+ * counts[3] == 1 bad label, [5] = counts[3] > 1 internal error, [6] = counts[1] raw entries needed) and copies them into
+ * the frontier slot's header; dm_slots_overflow sets *flag_dev when any gathered slot's entry count exceeds capacity. */
+int dm_shard_round_flags(const int64_t* counts, int64_t* flags, int first_round, int64_t* slot_flags, dm_stream_t stream);
+int dm_slots_overflow(const void* slots, int64_t n_slots, int64_t slot_bytes, int64_t capacity, int64_t* flag_dev,
+                      dm_stream_t stream);
+int dm_peer_put_slot(const void* slot, const int64_t* peer_bases_dev, int64_t world, int64_t rank, int64_t slot_bytes,
+                     int64_t header_bytes, int64_t seg0_offset, int64_t seg0_elem_bytes, int64_t seg1_offset,
+                     int64_t seg1_elem_bytes, int64_t capacity, dm_stream_t stream);
 int dm_mark_endpoints(const uint64_t* edge_keys, const int64_t* n_edges_dev, int64_t capacity, int64_t n_regions,
                       uint8_t* flags, dm_stream_t stream);
 int dm_rows_pack(const uint8_t* flag, const float* rows, int64_t n_regions, int64_t D, int32_t* out_ids,
