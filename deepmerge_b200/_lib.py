@@ -13,6 +13,8 @@ import re
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "deepmerge_b200.h")
 LIB_PATH = os.path.join(HERE, "libdeepmerge_b200.so")
+SYNTH_HEADER = os.path.join(os.path.dirname(HERE), "include", "deepmerge_b200_synth.h")
+SYNTH_LIB_PATH = os.path.join(HERE, "libdeepmerge_b200_synth.so")
 
 DM_OK, DM_ERR_BAD_ARG, DM_ERR_WORKSPACE, DM_ERR_CUDA, DM_ERR_UNSUPPORTED, DM_ERR_CAPACITY = 0, -1, -2, -3, -4, -5
 
@@ -49,19 +51,19 @@ def parse_header(path=HEADER):
 
 
 class Library:
-    def __init__(self, path=LIB_PATH):
+    def __init__(self, path=LIB_PATH, header=HEADER):
         if not os.path.exists(path):
             raise RuntimeError(
                 f"{path} not found: build it with `python -m deepmerge_b200.build` "
                 "(deepmerge_b200 has no CPU or PyTorch fallback)")
         self.path = path
         self.cdll = ctypes.CDLL(path)
-        self.protos = parse_header()
+        self.protos = parse_header(header)
         for name, (restype, argtypes, _) in self.protos.items():
             try:
                 fn = getattr(self.cdll, name)
             except AttributeError as e:
-                raise RuntimeError(f"{path} does not export {name} declared in {HEADER}") from e
+                raise RuntimeError(f"{path} does not export {name} declared in {header}") from e
             fn.restype = restype
             fn.argtypes = argtypes
             setattr(self, name, fn)
@@ -69,15 +71,25 @@ class Library:
     def check(self, rc, what=""):
         if rc == DM_OK:
             return
-        msg = self.dm_error_string(rc).decode()
+        msg = self.dm_error_string(rc).decode() if hasattr(self, "dm_error_string") else "error %d" % rc
         if rc == DM_ERR_BAD_ARG:
             raise ValueError(f"{what}: {msg}")
         if rc == DM_ERR_CUDA:
-            raise RuntimeError(f"{what}: {msg}: cudaError {self.dm_last_cuda_error()}")
+            code = self.dm_last_cuda_error() if hasattr(self, "dm_last_cuda_error") else "?"
+            raise RuntimeError(f"{what}: {msg}: cudaError {code}")
         raise RuntimeError(f"{what}: {msg}")
 
 
 _LIB = None
+_SYNTH = None
+
+
+def synth_lib() -> Library:
+    """The scene generator of bench.py / the tests (libdeepmerge_b200_synth.so): not part of the product ABI."""
+    global _SYNTH
+    if _SYNTH is None:
+        _SYNTH = Library(SYNTH_LIB_PATH, SYNTH_HEADER)
+    return _SYNTH
 
 
 def lib() -> Library:

@@ -2,6 +2,21 @@
 // (jittered-grid Voronoi labels, object-coherent image bands and embeddings).
 // Bench / test utility: lets full-size scenes be created directly in HBM.
 #include "common.cuh"
+#include "../../include/deepmerge_b200_synth.h"
+
+// libdeepmerge_b200_synth.so is linked on its own (bench / test utility, see the header): the few helpers of the product
+// library it uses are defined here.
+namespace dm {
+thread_local int g_last_cuda_error = 0;
+long long g_launch_count = 0;
+int num_sms() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        return 148;
+    return n;
+}
+}  // namespace dm
+
 
 namespace dm {
 namespace synth {

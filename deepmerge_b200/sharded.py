@@ -467,8 +467,9 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
     rop = points_region(sc.labels[: y1 - y0], xs, ys_rel)
     feats = torch.empty((xs.shape[0], D), dtype=torch.float32, device=dev)
     # feats are hashed per GLOBAL point id so that the scene does not depend on the sharding
-    L.check(L.dm_synth_feats(_p(feats), _p(rop), _p(sc.region_obj), _p(mine.contiguous()), xs.shape[0], D, cfg["seed"],
-                             _stream()), "dm_synth_feats")
+    SL = _lib.synth_lib()
+    SL.check(SL.dm_synth_feats(_p(feats), _p(rop), _p(sc.region_obj), _p(mine.contiguous()), xs.shape[0], D, cfg["seed"],
+                               _stream()), "dm_synth_feats")
     image = sc.image[: y1 - y0] if sc.image is not None else None
     eng = ShardedMergeEngine(H, W, R, D, C, xs.shape[0], dist, dev)
 

@@ -6,7 +6,7 @@ from dataclasses import dataclass
 
 import torch
 
-from ._lib import lib
+from ._lib import synth_lib
 from .raster import _p, _stream, points_region
 
 
@@ -32,7 +32,7 @@ def synth_scene(H, W, R, C=4, P=4, D=100, seed=1234, device=None, rows=None, wit
     """Whole scene (rows=None) or the row range rows=(y0, y1) of it.  Points / feats are always
     the whole scene's (they are small); region_of_point needs the whole label raster, so for a
     row range it is left empty."""
-    L = lib()
+    L = synth_lib()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     g = grid_pitch(H, W, R)
     ncx, ncy = -(-W // g), -(-H // g)

@@ -11,7 +11,11 @@
  * Conventions
  *  - every pointer is a DEVICE pointer unless its name ends in _host;
  *  - the caller owns every buffer including workspaces (query *_workspace_bytes, allocate,
- *    pass); the library allocates nothing persistent and keeps no mutable global state;
+ *    pass); the library allocates nothing persistent and keeps no mutable state between calls -- except three
+ *    DIAGNOSTICS that no result depends on: dm_launch_count() (a process-wide counter, incremented atomically),
+ *    dm_last_cuda_error() and dm_rag_last_path() / dm_rag_last_encode_error() (thread-local: they describe the last call
+ *    of the calling thread).  Everything else is re-entrant: concurrent calls from different host threads on different
+ *    streams / devices are safe;
  *  - all work is enqueued on `stream` (a cudaStream_t) and is asynchronous;
  *  - variable-size results use capacity + device-side counts: `counts` arrays live on
  *    the device so that dependent calls chain without a host round trip;
@@ -345,22 +349,6 @@ int dm_contrastive_fwd_bwd(const float* a, const float* b, const int64_t* flag, 
                            float margin, float* loss, float* grad_a, float* grad_b, dm_stream_t stream);
 /* Row gather used by the pair sampler path (R10): out[i] = table[idx[i]]. */
 int dm_gather_rows(const float* table, int64_t D, const int64_t* idx, int64_t n, float* out, dm_stream_t stream);
-
-/* ----------------------------------------------------------------------------------- *
- * Synthetic scenes of SURVEY.md section 8(d), generated on the device bit-identically to
- * oracle/oracle_np.py (bench and test utility; not part of the reference's path).
- * ----------------------------------------------------------------------------------- */
-int dm_synth_labels(int32_t* labels, int64_t y0, int64_t rows, int64_t H, int64_t W, int64_t ld, int64_t pitch_g,
-                    uint32_t seed, dm_stream_t stream);
-int dm_synth_region_objects(int32_t* region_obj, int64_t H, int64_t W, int64_t pitch_g, uint32_t seed,
-                            dm_stream_t stream);
-int dm_synth_image(uint8_t* image, const int32_t* labels, int64_t y0, int64_t rows, int64_t W, int64_t ld,
-                   int64_t C, const int32_t* region_obj, uint32_t seed, dm_stream_t stream);
-int dm_synth_points(int32_t* xs, int32_t* ys, int64_t H, int64_t W, int64_t pitch_g, int64_t P, uint32_t seed,
-                    dm_stream_t stream);
-/* point_ids (nullable): global ids of the n_points rows (a row-tile shard passes the ids of its own points) */
-int dm_synth_feats(float* feats, const int32_t* region_of_point, const int32_t* region_obj, const int64_t* point_ids,
-                   int64_t n_points, int64_t D, uint32_t seed, dm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,16 @@ def test_every_declared_symbol_is_exported(L):
         assert hasattr(L.cdll, name)
 
 
+def test_the_scene_generator_is_a_library_of_its_own():
+    """dm_synth_* (bench / test data) are not part of the product ABI: their own header, their own .so."""
+    S = _lib.synth_lib()
+    assert set(S.protos) == {"dm_synth_labels", "dm_synth_region_objects", "dm_synth_image", "dm_synth_points", "dm_synth_feats"}
+    assert not any(n.startswith("dm_synth") for n in _lib.parse_header())
+    product = ctypes.CDLL(_lib.LIB_PATH)
+    assert not hasattr(product, "dm_synth_labels")
+    assert S.dm_synth_labels(None, 0, -1, 4, 4, 4, 1, 0, None) == _lib.DM_ERR_BAD_ARG
+
+
 def test_version_and_error_strings(L):
     assert L.dm_version() == 100
     assert L.dm_error_string(0) == b"ok"

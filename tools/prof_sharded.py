@@ -18,7 +18,8 @@ sc = synth_scene(H, W, R_t, C=4, device=dev, rows=(y0, y1 + (1 if halo else 0)))
 mine = points_in_tile(sc.ys, y0, y1); xs, ys = sc.xs[mine].contiguous(), (sc.ys[mine] - y0).contiguous()
 rop = points_region(sc.labels[: y1 - y0], xs, ys)
 feats = torch.empty((xs.shape[0], 100), device=dev)
-L.check(L.dm_synth_feats(_p(feats), _p(rop), _p(sc.region_obj), _p(mine.contiguous()), xs.shape[0], 100, 1234, _stream()), "f")
+SL = _lib.synth_lib()
+SL.check(SL.dm_synth_feats(_p(feats), _p(rop), _p(sc.region_obj), _p(mine.contiguous()), xs.shape[0], 100, 1234, _stream()), "f")
 eng = ShardedMergeEngine(H, W, sc.n_regions, 100, 4, xs.shape[0], dist, dev)
 run = lambda: eng.run(sc.labels, feats, 0.5, image_tile=sc.image[: y1 - y0], xs_local=xs, ys_local_rel=ys)
 for _ in range(3): run()
