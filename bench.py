@@ -122,7 +122,7 @@ def run_cpu_port(cfg, steps=1, warmup=0):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return float(np.mean(times)), res["merges"], sc["n_regions"]
+    return float(np.min(times)), res["merges"], sc["n_regions"]
 
 
 _BARRIER = None
@@ -136,42 +136,48 @@ def _cpu_init(barrier):
 
 
 def _cpu_worker(args):
-    """One process = one sample scene: generate it, meet the others at the barrier, then run the timed steps."""
-    cfg, steps = args
+    """One process = one sample scene: generate it, then `warmup` untimed and `steps` timed passes; every pass starts at
+    a barrier of all processes, and (start, end) of every timed pass is returned."""
+    cfg, steps, warmup = args
     from oracle import oracle_np as o
     sc = o.synth_scene(cfg["H"], cfg["W"], cfg["R"], C=cfg["C"], P=cfg["P"], D=cfg["D"], seed=cfg["seed"])
-    _BARRIER.wait()
-    t0 = time.time()
-    for _ in range(steps):
+    spans = []
+    for k in range(warmup + steps):
+        _BARRIER.wait()
+        t0 = time.time()
         res = o.merge_scene(sc["labels"], sc["n_regions"], sc["region_of_point"], sc["feats"], tau=cfg["tau"])
         o.pool_bands(sc["labels"], sc["image"], sc["n_regions"])
-    return t0, time.time(), res["merges"], sc["n_regions"]
+        if k >= warmup:
+            spans.append((t0, time.time()))
+    return spans, res["merges"], sc["n_regions"]
 
 
-def run_cpu_port_parallel(cfg, steps=1, procs=None):
+def run_cpu_port_parallel(cfg, steps=1, procs=None, warmup=1):
     """The oracle port on ALL host cores: the numpy path is single-threaded, so `procs` processes each
-    run it on their own sample scene (different seeds) side by side; throughput = pixels of all
-    samples / (last finish - first start).  Returns (seconds per step, merges of one sample, segments, procs)."""
+    run it on their own sample scene (different seeds) side by side; a pass takes (last finish - first start) over the
+    processes, and the BEST of the `steps` timed passes after `warmup` untimed ones is reported (BASELINE.md section 4:
+    one warm-up, best of 3).  Returns (seconds per step, merges of one sample, segments, procs)."""
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64) if procs is None else procs)
     if procs == 1:
-        sec, merges, R = run_cpu_port(cfg, steps=steps)
+        sec, merges, R = run_cpu_port(cfg, steps=steps, warmup=warmup)
         return sec, merges, R, 1
     ctx = mp.get_context("spawn")
-    jobs = [(dict(cfg, seed=cfg["seed"] + i), steps) for i in range(procs)]
+    jobs = [(dict(cfg, seed=cfg["seed"] + i), steps, warmup) for i in range(procs)]
     with ctx.Pool(procs, initializer=_cpu_init, initargs=(ctx.Barrier(procs),)) as pool:
         out = pool.map(_cpu_worker, jobs, chunksize=1)
-    wall = max(o[1] for o in out) - min(o[0] for o in out)
-    return wall / steps, out[0][2], out[0][3], procs
+    walls = [max(o[0][k][1] for o in out) - min(o[0][k][0] for o in out) for k in range(steps)]
+    return min(walls), out[0][1], out[0][2], procs
 
 
-def cpu_baseline_record(cfg, side, steps=1):
+def cpu_baseline_record(cfg, side, steps=3, warmup=1):
     ccfg = cpu_sample_dims(cfg, side)
-    sec, merges, R, procs = run_cpu_port_parallel(ccfg, steps=steps)
+    sec, merges, R, procs = run_cpu_port_parallel(ccfg, steps=steps, warmup=warmup)
     mpx = procs * ccfg["H"] * ccfg["W"] / sec / 1e6
     sample = (f"{procs} x {ccfg['H']}x{ccfg['W']} scenes at the workload's region pitch ({R} segments each), "
-              f"{ccfg['C']} bands; numpy oracle port, one process per scene on {procs} of {os.cpu_count()} host cores")
+              f"{ccfg['C']} bands; numpy oracle port, one process per scene on {procs} of {os.cpu_count()} host cores; "
+              f"{warmup} warm-up pass, best of {steps}")
     return {"value": mpx, "unit": "Mpx/s", "cores": procs, "kind": "port", "sample": sample}, sec, merges * procs
 
 
@@ -179,8 +185,8 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), 0
-    rec, sec, merges = cpu_baseline_record(CFG, args.cpu_side, steps=steps)
+    steps, warmup = max(1, min(args.steps, 3)), min(max(args.warmup, 0), 1)
+    rec, sec, merges = cpu_baseline_record(CFG, args.cpu_side, steps=steps, warmup=warmup)
     line = {
         "impl": "reference", "metric": "megapixels/sec end-to-end (RAG+pool+score+merge+relabel)", "value": rec["value"],
         "unit": "Mpx/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
@@ -465,7 +471,7 @@ def b200_arm(args):
     # ---- CPU baseline: the oracle port on a bounded sample, same box, all host cores ---------------------------
     cpu = None
     if not args.no_cpu:
-        cpu, _, _ = cpu_baseline_record(cfg, min(args.cpu_side, H))
+        cpu, _, _ = cpu_baseline_record(cfg, min(args.cpu_side, H), steps=3, warmup=1)
 
     line = {
         "metric": "megapixels/sec end-to-end (RAG+pool+score+merge+relabel)", "value": mpx, "unit": "Mpx/s",
@@ -480,10 +486,11 @@ def b200_arm(args):
                 "d2h_bytes_per_step": d2h, "api": "ScenePipeline.run (H2D / compute / D2H of neighbouring steps overlap)",
                 "unpipelined_ms_per_step": e2e_single_ms, "unpipelined_value": H * W / e2e_single_ms / 1e3},
         "gpu_launches": launches,
-        "roofline": {"kernel": "rag_pool_kernel (fused RAG + band pooling raster pass)", "bound": "hbm",
+        "roofline": {"kernel": "rag_blocks_kernel (fused RAG + band pooling raster pass)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                      "frac_of_nominal_8TBs": achieved / 8000.0, "ms": rag_ms, "algorithmic_bytes": alg_bytes,
-                     "traffic": ncu_traffic("rag_pool_kernel") if not args.side else None},
+                     "traffic": ncu_traffic("rag_blocks_kernel") if not args.side else None,
+                     "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel on this workload)"},
         "mlp": mlp_rec, "mlp_step": mlp_step, "multi_round": multi, "train_pairs": train, "cpu_baseline": cpu,
         "clocks": clocks.summary(),
     }

@@ -528,7 +528,25 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
     dist.barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
     eng.eng.out = pipe.dev_out[0]
+    # what the host side can deliver when all ranks copy at once (copies only, no compute): the ceiling of the e2e figure
+    def link_gbs(fn, nbytes, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t1 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return nbytes * reps / (time.perf_counter() - t1) / 1e9
+    dev_in = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    dev_lab = torch.empty((y1 - y0, W), dtype=torch.int32, device=dev)
+    link_h2d = link_gbs(lambda: [dev_in[k].copy_(host[k], non_blocking=True) for k in host], h2d)
+    link_d2h = link_gbs(lambda: out_host.copy_(dev_lab, non_blocking=True), out_host.numel() * 4)
+    del dev_in, dev_lab
     t = torch.tensor([e2e_ms, float(h2d), float(out_host.numel() * 4)], dtype=torch.float64, device=dev)
+    lk = torch.tensor([link_h2d, link_d2h], dtype=torch.float64, device=dev)
+    lk_min = lk.clone()
+    dist.all_reduce(lk_min, op=dist.ReduceOp.MIN)
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -598,7 +616,12 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
             "ms_per_step_gathered": ms_gathered,
             "e2e": {"value": H * W / float(tmax[0]) / 1e3, "unit": "Mpx/s", "ms_per_step": float(tmax[0]),
                     "h2d_bytes_per_step": int(t[1]), "d2h_bytes_per_step": int(t[2]),
-                    "api": "ScenePipeline over ShardedMergeEngine.run: every rank overlaps its tile's H2D / compute / D2H"},
+                    "api": "ScenePipeline over ShardedMergeEngine.run: every rank overlaps its tile's H2D / compute / D2H",
+                    "per_gpu_h2d_gbs": h2d / (float(tmax[0]) * 1e-3) / 1e9, "per_gpu_d2h_gbs": out_host.numel() * 4 / (float(tmax[0]) * 1e-3) / 1e9,
+                    "copy_only_h2d_gbs_per_gpu_all_ranks_at_once": float(lk_min[0]),
+                    "copy_only_d2h_gbs_per_gpu_all_ranks_at_once": float(lk_min[1]),
+                    "note": "copy_only_* = pinned host <-> device copies of the same buffers with every rank copying at the same "
+                            "time and nothing else running (slowest rank): the host side's ceiling for this step"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "rag_pool_kernel (fused RAG + band pooling raster pass), rank 0's tile", "bound": "hbm",
                          "achieved": alg / (rag_ms * 1e-3) / 1e9, "peak": peak, "peak_kind": kind, "unit": "GB/s",
