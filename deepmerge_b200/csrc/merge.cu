@@ -450,9 +450,9 @@ __global__ void shard_round_flags_kernel(const int64_t* __restrict__ counts, int
     if (first_round) {
         if (i == 3) v = counts[2] != 0;
         if (i == 4) v = counts[3] == 1;
-        if (i == 5) v = counts[3] > 1;
         if (i == 6) v = counts[1];
     }
+    if (i == 5 && counts[3] > 1) v = 1;                       // internal error (raster pass, pair-MLP status): any round
     flags[i] = v;
     slot_flags[i] = v;
 }

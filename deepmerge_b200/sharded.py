@@ -245,14 +245,17 @@ class ShardedMergeEngine:
         return self.host_fflags.tolist(), e.host_counts.tolist()
 
     def run(self, labels_tile, feats_local, tau, *, image_tile=None, xs_local=None, ys_local_rel=None, max_rounds=64,
-            gather_outputs=True):
+            gather_outputs=True, mlp=None):
         """labels_tile: int32 [rows_own (+1 halo), W]; ys_local_rel are rows relative to the tile.
 
         The result is DISTRIBUTED unless gather_outputs: labels = this tile's label map, root / cnt replicated,
         edge_keys / boundary_len = this tile's final edge list (the global list is the union, lengths add up),
         area / perimeter (and the engine's band sums) = this tile's partials (they add up over ranks), sum = rows of
         the regions this rank sees.  gather_outputs=True all-reduces the statistics and gathers + uniques the edge
-        lists so that every rank holds the same MergeResult a single GPU would produce."""
+        lists so that every rank holds the same MergeResult a single GPU would produce.
+
+        mlp (a PackedMLP, replicated on every rank): the tcgen05 pair-MLP scores every live tile edge every round and an edge
+        is selected when argmax(o) == 1 (Nets.py:28-35) instead of L2 distance < tau -- as MergeEngine.run(mlp=...) does."""
         from .raster import MergeResult, _p, _stream
         e, L, dist, grp = self.eng, self.eng.L, self.dist, self.group
         R, D, cap = e.R, e.D, e.cap
@@ -286,11 +289,17 @@ class ShardedMergeEngine:
             e.alive.fill_(1)
             e.counts[5:8].zero_()
             L.check(L.dm_region_mean(_p(e.sum), _p(e.cnt), R, D, _p(e.mean), _p(e.norm2), _p(self.seen), s), "dm_region_mean")
-            L.check(L.dm_score_l2(_p(e.mean), _p(e.norm2), D, _p(e.keys), _p(n_edges), cap, None, _p(e.scores), s), "dm_score_l2")
+            if mlp is not None and mlp.in_features != 2 * D:
+                raise ValueError("the pair-MLP takes concat(mean[lo], mean[hi]): in_features must be 2 D")
+            e._score(mlp, None)
             rounds = merges = 0
             while True:
-                L.check(L.dm_merge_select_l2(_p(e.scores), float(tau), _p(n_edges), cap, _p(e.selected),
-                                             e.counts[4:5].data_ptr(), s), "dm_merge_select_l2")
+                if mlp is None:
+                    L.check(L.dm_merge_select_l2(_p(e.scores), float(tau), _p(n_edges), cap, _p(e.selected),
+                                                 e.counts[4:5].data_ptr(), s), "dm_merge_select_l2")
+                else:
+                    L.check(L.dm_merge_select_mlp(_p(e.logits), mlp.n_out, _p(n_edges), cap, _p(e.selected),
+                                                  e.counts[4:5].data_ptr(), s), "dm_merge_select_mlp")
                 # Union-find of the round, prepared BEFORE anyone knows whether the round takes place: local unions, then the
                 # frontier pairs (shared component, its local root).  The pairs of all ranks carry the whole cross-tile
                 # connectivity -- no iteration, no convergence test -- and the round's flags ("edges selected", errors)
@@ -340,8 +349,7 @@ class ShardedMergeEngine:
                                          _p(e.ws), e.ws_bytes, s), "dm_edges_rekey")
                 cur.wait_stream(e.side)
                 L.check(L.dm_region_mean(_p(e.sum), _p(e.cnt), R, D, _p(e.mean), _p(e.norm2), _p(e.changed), s), "dm_region_mean")
-                L.check(L.dm_score_l2(_p(e.mean), _p(e.norm2), D, _p(e.keys), _p(n_edges), cap, _p(e.changed), _p(e.scores), s),
-                        "dm_score_l2")
+                e._score(mlp, e.changed)
             # (5) tile-local relabel with the replicated root LUT
             L.check(L.dm_relabel(_p(labels_tile), self.rows_own, self.W, labels_tile.stride(0), _p(e.parent), R, _p(e.out),
                                  self.W, s), "dm_relabel")

@@ -321,7 +321,7 @@ int dm_uf_union_slots(int32_t* parent, const void* slots, int64_t n_slots, int64
  * barrier that follows its last read).  All offsets / sizes in bytes, multiples of 16 where they are addresses. */
 /* host-side glue of the distributed loop as single launches: dm_shard_round_flags fills the eight flag words of a round
  * from the engine's counters (flags[0] = counts[4] edges selected; first round also [3] = counts[2] != 0 overflow, [4] =
- * counts[3] == 1 bad label, [5] = counts[3] > 1 internal error, [6] = counts[1] raw entries needed) and copies them into
+ * counts[3] == 1 bad label, [6] = counts[1] raw entries needed; every round [5] |= counts[3] > 1 internal error) and copies them into
  * the frontier slot's header; dm_slots_overflow sets *flag_dev when any gathered slot's entry count exceeds capacity. */
 int dm_shard_round_flags(const int64_t* counts, int64_t* flags, int first_round, int64_t* slot_flags, dm_stream_t stream);
 int dm_slots_overflow(const void* slots, int64_t n_slots, int64_t slot_bytes, int64_t capacity, int64_t* flag_dev,

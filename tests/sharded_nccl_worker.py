@@ -52,6 +52,35 @@ def main():
             roots = np.unique(want["root"])
             ok = ok and np.array_equal(res.area.cpu().numpy()[roots], want["area"][roots])
             ok = ok and np.array_equal(res.edge_keys.cpu().numpy().view(np.uint64), want["keys"])
+    # the pair-MLP as the scorer of the distributed loop (a hand-made "same object?" network with wide logit margins)
+    from deepmerge_b200 import PackedMLP
+    H, W, R = 400, 512, 900
+    sc = o.synth_scene(H, W, R, C=4)
+    n, D = sc["n_regions"], sc["feats"].shape[1]
+    W1 = np.zeros((2 * D, 2 * D), np.float32)
+    for d in range(D):
+        W1[d, d], W1[d, D + d] = 1, -1
+        W1[D + d, d], W1[D + d, D + d] = -1, 1
+    W3 = np.zeros((2, 2 * D), np.float32)
+    W3[0] = 1.0
+    Wm = [W1, np.zeros(2 * D, np.float32), np.eye(2 * D, dtype=np.float32), np.zeros(2 * D, np.float32), W3,
+          np.array([0.0, 4.0], np.float32)]
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    y0, y1 = tile_bounds(H, world, rank)
+    last = rank == world - 1
+    mine = points_in_tile(torch.from_numpy(sc["ys"]), y0, y1).numpy()
+    eng = ShardedMergeEngine(H, W, n, D, 4, len(mine), dist, dev)
+    res = eng.run(T(sc["labels"][y0:y1 + (0 if last else 1)]), T(sc["feats"][mine]), 0.0, image_tile=T(sc["image"][y0:y1]),
+                  xs_local=T(sc["xs"][mine]), ys_local_rel=T(sc["ys"][mine] - y0), gather_outputs=False,
+                  mlp=PackedMLP(*[T(w) for w in Wm]))
+    want = o.merge_scene(sc["labels"], n, sc["region_of_point"], sc["feats"], mlp=tuple(Wm))
+    mine_ok = bool(np.array_equal(res.labels.cpu().numpy(), want["labels"][y0:y1])) and \
+        bool(np.array_equal(res.root.cpu().numpy(), want["root"])) and res.merges == want["merges"] and want["merges"] > 0
+    okt = torch.tensor([1 if mine_ok else 0], device=dev)
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if rank == 0 and not int(okt.item()):
+        print("MISMATCH in the MLP-scored sharded merge", flush=True)
+    ok = ok and bool(int(okt.item()))
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     if rank == 0 and ok:
