@@ -468,6 +468,58 @@ def b200_arm(args):
     except Exception as ex:
         train = {"error": repr(ex)}
 
+    # ---- configs[0]: 1024 x 1024, 3 bands, ~2k segments, MLP merge -- next to the reference-STYLE CPU path --------------
+    # (the embeddings are the synthetic ones: the ShiftScaleFormer that produces them in the reference is outside this
+    # build, and it is left out of BOTH arms)
+    config0 = None
+    try:
+        s0 = synth_scene(1024, 1024, 2000, C=3, P=cfg["P"], D=D, seed=cfg["seed"], device=dev)
+        e0 = MergeEngine(1024, 1024, s0.n_regions, D, C=3, n_points=s0.feats.shape[0], device=dev)
+
+        def step0(mlp_):
+            return e0.run(s0.labels, s0.feats, 0.0 if mlp_ is not None else cfg["tau"], image=s0.image, xs=s0.xs, ys=s0.ys, mlp=mlp_)
+
+        rec0 = {}
+        for name, m_ in (("mlp", l1net), ("l2", None)):
+            for _ in range(3):
+                r0 = step0(m_)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(20):
+                r0 = step0(m_)
+            ev1.record()
+            torch.cuda.synchronize()
+            rec0[name] = {"ms_per_step": ev0.elapsed_time(ev1) / 20, "rounds": r0.rounds, "merges": r0.merges}
+        # reference-style CPU path: the per-edge loop of ExtractFeatures.py:164-222, one thread
+        cpu0 = None
+        if not args.no_cpu:
+            from oracle import oracle_np as o
+            g0 = e0.run(s0.labels, s0.feats, cfg["tau"], image=s0.image, xs=s0.xs, ys=s0.ys, max_rounds=0)
+            k0h = g0.edge_keys.cpu().numpy()
+            lo0, hi0 = (k0h >> 32).astype(np.int64), (k0h & 0xFFFFFFFF).astype(np.int64)
+            rop0 = s0.region_of_point.cpu().numpy()
+            off0, ids0 = o.csr_from_region_of_point(rop0, s0.n_regions)
+            fields0 = [" ".join(str(int(v)) for v in ids0[off0[r]:off0[r + 1]]) for r in range(s0.n_regions)]
+            ok = np.array([fields0[a] != "" and fields0[b] != "" for a, b in zip(lo0, hi0)])
+            store0 = s0.feats.cpu().numpy()
+            t0 = time.perf_counter()
+            simi0 = o.edge_loop_reference_style(store0, fields0, lo0[ok], hi0[ok])
+            loop_s = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            o.merge_scene(s0.labels.cpu().numpy(), s0.n_regions, rop0, store0, tau=cfg["tau"])
+            port_s = time.perf_counter() - t0
+            cpu0 = {"reference_style_edge_loop_s": loop_s, "edges": int(ok.sum()), "edges_per_s": float(ok.sum()) / loop_s,
+                    "kind": "port of ExtractFeatures.py:164-222 (per-edge gather by np.concatenate, np.mean, Euclidean_distance), "
+                            "1 host core, scores only", "vectorised_port_whole_step_s": port_s,
+                    "max_abs_diff_vs_gpu_scores": float(np.nanmax(np.abs(simi0 - g0.scores.cpu().numpy()[: len(k0h)][ok])))}
+        config0 = {"workload": "configs[0]: 1024 x 1024 3-band tile, %d segments, %d edges, synthetic embeddings (no ShiftScaleFormer in "
+                               "either arm)" % (s0.n_regions, int(e0.run(s0.labels, s0.feats, cfg["tau"], image=s0.image, xs=s0.xs, ys=s0.ys,
+                                                                          max_rounds=0).edge_keys.shape[0])),
+                   "gpu_step_pair_mlp": rec0["mlp"], "gpu_step_l2": rec0["l2"], "cpu": cpu0}
+        del e0, s0
+    except Exception as ex:
+        config0 = {"error": repr(ex)}
+
     # ---- CPU baseline: the oracle port on a bounded sample, same box, all host cores ---------------------------
     cpu = None
     if not args.no_cpu:
@@ -491,7 +543,7 @@ def b200_arm(args):
                      "frac_of_nominal_8TBs": achieved / 8000.0, "ms": rag_ms, "algorithmic_bytes": alg_bytes,
                      "traffic": ncu_traffic("rag_blocks_kernel") if not args.side else None,
                      "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel on this workload)"},
-        "mlp": mlp_rec, "mlp_step": mlp_step, "multi_round": multi, "train_pairs": train, "cpu_baseline": cpu,
+        "mlp": mlp_rec, "mlp_step": mlp_step, "multi_round": multi, "train_pairs": train, "config0": config0, "cpu_baseline": cpu,
         "clocks": clocks.summary(),
     }
     print(json.dumps(line), flush=True)

@@ -417,6 +417,30 @@ def euclidean_distance(X, Y):
     return np.sqrt(D)
 
 
+def edge_loop_reference_style(store, point_id_fields, left_ids, right_ids):
+    """The reference's OWN shape of the scoring path, one edge at a time (ExtractFeatures.py:164-222 minus the OGR / h5py
+    I/O and the `break` at :223): for every edge gather the member rows of both polygons by repeated np.concatenate
+    (:190-207), np.mean(axis=0) (:211-212), Euclidean_distance on two [1, D] rows (:215) and keep D.max() (:216).  Nothing
+    is cached: a polygon is re-pooled for every incident edge, as there.  This is the "reference-style path" of BASELINE.md
+    section 4.1 that bench.py times as the CPU arm of configs[0]; pinned against the executed reference through the golden
+    pool_score.npz (tests/test_oracle_golden.py).  -> simi float64 [E]."""
+    simi = np.zeros(len(left_ids), np.float64)
+    for e in range(len(left_ids)):
+        left_poly_samples = str(point_id_fields[int(left_ids[e])]).split(" ")
+        right_poly_samples = str(point_id_fields[int(right_ids[e])]).split(" ")
+        out_left_data, out_right_data = [], []
+        for m in range(len(left_poly_samples)):
+            row = store[int(left_poly_samples[m])][np.newaxis, :]
+            out_left_data = row if m == 0 else np.concatenate((out_left_data, row), axis=0)
+        for n in range(len(right_poly_samples)):
+            row = store[int(right_poly_samples[n])][np.newaxis, :]
+            out_right_data = row if n == 0 else np.concatenate((out_right_data, row), axis=0)
+        out_left_data = np.mean(out_left_data, axis=0)
+        out_right_data = np.mean(out_right_data, axis=0)
+        simi[e] = float(euclidean_distance(out_left_data[np.newaxis, :], out_right_data[np.newaxis, :]).max())
+    return simi
+
+
 def score_l2(mean, keys):
     """R6 for every edge: the reference's expanded formula, fp32, one (lo,hi) pair per row."""
     lo, hi = unpack_keys(keys)

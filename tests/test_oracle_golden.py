@@ -228,3 +228,10 @@ def test_patch_resize_against_opencv_when_installed():
             a = rng.integers(0, 256, (s, s), dtype=np.uint8)
             want = cv2.resize(a, (t, t), interpolation=cv2.INTER_AREA).reshape(t, t)
             assert np.array_equal(resize_area_u8(a, t), want), (s, t)
+
+
+def test_reference_style_edge_loop_equals_the_executed_reference(golden_dir):
+    """The per-edge loop bench.py times as the CPU arm of configs[0] reproduces the executed reference's `simi` values."""
+    g = np.load(os.path.join(golden_dir, "pool_score.npz"))
+    simi = o.edge_loop_reference_style(g["store"], list(g["fields"]), g["left"], g["right"])
+    assert np.array_equal(simi, g["simi"])
