@@ -264,6 +264,51 @@ static unsigned grid_for(int64_t work_items, int threads, int per_sm) {
     return (unsigned)imax64(1, min(g, cap));
 }
 
+// N2: bounding boxes of the regions (for the designed attributes len / width / smooth / compact / border, MyUtils1.py:79-114).
+// A warp walks down a 32-pixel column strip; a lane keeps the vertical run of its column (label, first row) and publishes
+// it with four integer atomics when the label changes: min / max column, first / last row.
+__global__ void __launch_bounds__(256) region_bbox_kernel(const int32_t* __restrict__ labels, int64_t H, int64_t W, int64_t ld,
+                                                          int64_t R, int32_t* __restrict__ bbox, int rows_per_warp,
+                                                          unsigned long long* __restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t strips = (W + 31) / 32, chunks = (H + rows_per_warp - 1) / rows_per_warp;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = warp0; w < strips * chunks; w += nwarps) {
+        const int64_t sx = w % strips, cy = w / strips;
+        const int64_t x = sx * 32 + lane, y0 = cy * rows_per_warp, y1 = imin64(H, y0 + rows_per_warp);
+        if (x >= W) continue;
+        int cur = -1;
+        int64_t ys = y0;
+        auto flush = [&](int64_t ylast) {
+            if (cur < 0) return;
+            if (cur >= R) { atomicExch(bad, 1ull); return; }
+            int32_t* b = bbox + (int64_t)cur * 4;
+            atomicMin(&b[0], (int)x);
+            atomicMin(&b[1], (int)ys);
+            atomicMax(&b[2], (int)x);
+            atomicMax(&b[3], (int)ylast);
+        };
+        for (int64_t y = y0; y < y1; ++y) {
+            const int l = labels[y * ld + x];
+            if (l != cur) {
+                flush(y - 1);
+                cur = l;
+                ys = y;
+            }
+        }
+        flush(y1 - 1);
+    }
+}
+__global__ void region_bbox_init_kernel(int32_t* __restrict__ bbox, int64_t R) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x) {
+        bbox[4 * r] = 0x7fffffff;
+        bbox[4 * r + 1] = 0x7fffffff;
+        bbox[4 * r + 2] = -1;
+        bbox[4 * r + 3] = -1;
+    }
+}
+
 }  // namespace pool
 }  // namespace dm
 
@@ -402,6 +447,25 @@ extern "C" int dm_cut_windows(const uint8_t* image, int64_t C, int64_t H, int64_
     if (!image || !x0 || !y0 || !out) return DM_ERR_BAD_ARG;
     DM_COUNT_LAUNCH(); pool::cut_windows_kernel<<<pool::grid_for(n * C * size * 32, 256, 8), 256, 0, S(stream)>>>(image, (int)C, H, W, x0, y0, n,
                                                                                            (int)size, out);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_region_bbox(const int32_t* labels, int64_t H, int64_t W, int64_t ld, int64_t n_regions, int32_t* bbox,
+                              int64_t* bad_label, dm_stream_t stream) {
+    if (H < 0 || W < 0 || ld < W || n_regions < 0 || H > 0x7ffffff0 || W > 0x7ffffff0) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    if (bad_label) DM_CUDA(cudaMemsetAsync(bad_label, 0, sizeof(int64_t), s));
+    if (n_regions == 0) return DM_OK;
+    if (!bbox || !bad_label) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); pool::region_bbox_init_kernel<<<pool::grid_for(n_regions, 256, 8), 256, 0, s>>>(bbox, n_regions);
+    if (H > 0 && W > 0) {
+        if (!labels) return DM_ERR_BAD_ARG;
+        const int rows_per_warp = 128;
+        const int64_t warps = ceil_div(W, 32) * ceil_div(H, rows_per_warp);
+        DM_COUNT_LAUNCH(); pool::region_bbox_kernel<<<pool::grid_for(warps * 32, 256, 8), 256, 0, s>>>(
+            labels, H, W, ld, n_regions, bbox, rows_per_warp, (unsigned long long*)bad_label);
+    }
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

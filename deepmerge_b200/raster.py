@@ -50,6 +50,7 @@ class RAG:
     border: torch.Tensor          # int64 [R] sides facing the image border / nodata
     band_sum: Optional[torch.Tensor] = None    # int64 [R, C] (uint64 values)
     band_sumsq: Optional[torch.Tensor] = None  # int64 [R, C]
+    bbox: Optional[torch.Tensor] = None        # int32 [R, 4] (min col, min row, max col, max row); build_rag(bbox=True)
 
     @property
     def n_edges(self):
@@ -62,10 +63,30 @@ class RAG:
         """The designed polygon attributes of the reference's tables (MyUtils1.py:79-114) that follow from this
         pass alone (first part): `area` (pixels), `peri` (pixel sides facing another label, nodata
         or the image border), per band `mean<c>` and `std<c>` (population deviation) and `bright` (mean of the band
-        means) -> dict of float32 tensors [R] ([R, C] for mean / std), NaN for regions without pixels.  The
-        bounding-box attributes (len, width, smooth, shapeness, compact, border) are not produced yet."""
+        means) -> dict of float32 tensors [R] ([R, C] for mean / std), NaN for regions without pixels.
+
+        With `bbox` (build_rag(..., bbox=True)) the bounding-box attributes follow.  The reference only READS these
+        columns (they were written by the segmentation software, their formulas are not in the repository), so the
+        definitions are this build's, the usual object-based ones, restated in oracle_np.shape_attributes:
+        `len` / `width` = longer / shorter side of the axis-aligned bounding box in pixels, `smooth` = peri over the
+        bounding box's border 2 (w + h), `shapeness` = peri / (4 sqrt(area)), `compact` = len * width / area,
+        `border` = peri / (2 (len + area / len))."""
         area = self.area.to(torch.float64)
         out = {"area": area.to(_F32), "peri": self.perimeter.to(_F32)}
+        if self.bbox is not None:
+            b = self.bbox.to(torch.float64)
+            nan = torch.full_like(area, float("nan"))
+            has = area > 0
+            w = torch.where(has, b[:, 2] - b[:, 0] + 1, nan)
+            h = torch.where(has, b[:, 3] - b[:, 1] + 1, nan)
+            a = torch.where(has, area, nan)
+            peri = self.perimeter.to(torch.float64)
+            ln, wd = torch.maximum(w, h), torch.minimum(w, h)
+            out["len"], out["width"] = ln.to(_F32), wd.to(_F32)
+            out["smooth"] = (peri / (2.0 * (w + h))).to(_F32)
+            out["shapeness"] = (peri / (4.0 * torch.sqrt(a))).to(_F32)
+            out["compact"] = (ln * wd / a).to(_F32)
+            out["border"] = (peri / (2.0 * (ln + a / ln))).to(_F32)
         if self.band_sum is not None:
             n = torch.where(area > 0, area, torch.full_like(area, float("nan")))[:, None]
             mean = self.band_sum.to(torch.float64) / n
@@ -81,7 +102,7 @@ def default_edge_capacity(n_regions, H, W):
 
 
 def build_rag(labels: torch.Tensor, n_regions: int, image: Optional[torch.Tensor] = None, *, rows_own=None,
-              top_border=True, bottom_border=True, capacity=None, return_raw=False) -> RAG:
+              top_border=True, bottom_border=True, capacity=None, return_raw=False, bbox=False) -> RAG:
     """RAG of a label raster, fused with band pooling when `image` (uint8 [H,W,C]) is given.
 
     Replaces the edge list the reference reads from lines.shp (MyUtils2.py:155-193) and the
@@ -129,9 +150,28 @@ def build_rag(labels: torch.Tensor, n_regions: int, image: Optional[torch.Tensor
         L.check(L.dm_perimeter(_p(keys), _p(blen), _p(counts), cap, _p(border), _p(perim), n_regions, _stream()),
                 "dm_perimeter")
     rag = RAG(keys[:E], blen[:E], area, perim, border, bsum, bsq)
+    if bbox:
+        rag.bbox = region_bbox(labels[:own], n_regions)
     if return_raw:
         return rag, int(c[1])
     return rag
+
+
+def region_bbox(labels, n_regions):
+    """Bounding box of every region -> int32 [R, 4] (min column, min row, max column, max row; (INT32_MAX, INT32_MAX,
+    -1, -1) for a region without pixels).  Input of the bounding-box attributes of RAG.attributes."""
+    L = lib()
+    labels = _labels_2d(labels)
+    _need_cuda(labels)
+    H, W = labels.shape
+    with torch.cuda.device(labels.device):
+        box = torch.empty((n_regions, 4), dtype=_I32, device=labels.device)
+        bad = torch.zeros(1, dtype=_I64, device=labels.device)
+        L.check(L.dm_region_bbox(_p(labels), H, W, labels.stride(0), n_regions, _p(box), _p(bad), _stream()),
+                "dm_region_bbox")
+        if int(bad.item()):
+            raise ValueError("labels contain ids >= n_regions")
+    return box
 
 
 def pool_bands(labels, image, n_regions):

@@ -341,6 +341,15 @@ int dm_rows_unpack_slots(const void* slots, int64_t n_slots, int64_t slot_bytes,
                          int64_t n_regions, int64_t D, float* rows, int zero, dm_stream_t stream);
 
 /* ----------------------------------------------------------------------------------- *
+ * N2  Bounding boxes of the regions, for the bounding-box attributes of the reference's polygon tables (len, width, smooth,
+ *     compact, border; MyUtils1.py:79-114 reads them, their formulas are not in the repository: DESIGN.md section 4.5).
+ *     bbox int32 [R, 4] = (min column, min row, max column, max row), (INT32_MAX, INT32_MAX, -1, -1) for a region
+ *     without pixels; *bad_label != 0 when a label >= n_regions was met.  Not part of the merge step.
+ * ----------------------------------------------------------------------------------- */
+int dm_region_bbox(const int32_t* labels, int64_t H, int64_t W, int64_t ld, int64_t n_regions, int32_t* bbox,
+                   int64_t* bad_label, dm_stream_t stream);
+
+/* ----------------------------------------------------------------------------------- *
  * R11 Contrastive pair loss forward + backward (Losses.py:34-38):
  *     d = sum_k (a-b)^2 ; L = mean(flag*d + (1-flag)*relu(margin-d)).
  *     loss fp32 [1]; grad_a, grad_b fp32 [B,D] (nullable).  flag int64 as collated.

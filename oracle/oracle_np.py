@@ -647,3 +647,36 @@ def merge_scene(labels, n_regions, region_of_point, feats, tau=None, mlp=None, m
     g["labels"] = relabel(labels, g["root"])
     g["keys0"], g["blen0"], g["area0"], g["perim0"] = keys, blen, area, perim
     return g
+
+
+def region_bbox(labels, n_regions):
+    """N2: bounding box of every region -> int32 [R, 4] (min column, min row, max column, max row), (INT32_MAX, INT32_MAX,
+    -1, -1) without pixels.  The reference reads the attributes derived from it from polygons.shp (MyUtils1.py:79-114)."""
+    lab = np.asarray(labels)
+    H, W = lab.shape
+    box = np.empty((n_regions, 4), np.int32)
+    box[:, :2] = np.iinfo(np.int32).max
+    box[:, 2:] = -1
+    ys, xs = np.nonzero(lab >= 0)
+    l = lab[ys, xs]
+    np.minimum.at(box[:, 0], l, xs.astype(np.int32))
+    np.minimum.at(box[:, 1], l, ys.astype(np.int32))
+    np.maximum.at(box[:, 2], l, xs.astype(np.int32))
+    np.maximum.at(box[:, 3], l, ys.astype(np.int32))
+    return box
+
+
+def shape_attributes(area, perimeter, bbox):
+    """N2: the bounding-box attributes as this build defines them (the reference's tables were written by the
+    segmentation software; MyUtils1.py:79-114 only reads the columns) -> dict of float32 [R], NaN without pixels."""
+    a = np.asarray(area, np.float64).copy()
+    a[a <= 0] = np.nan
+    b = np.asarray(bbox, np.float64)
+    w = np.where(np.isnan(a), np.nan, b[:, 2] - b[:, 0] + 1)
+    h = np.where(np.isnan(a), np.nan, b[:, 3] - b[:, 1] + 1)
+    p = np.asarray(perimeter, np.float64)
+    ln, wd = np.maximum(w, h), np.minimum(w, h)
+    f = np.float32
+    return {"len": ln.astype(f), "width": wd.astype(f), "smooth": (p / (2.0 * (w + h))).astype(f),
+            "shapeness": (p / (4.0 * np.sqrt(a))).astype(f), "compact": (ln * wd / a).astype(f),
+            "border": (p / (2.0 * (ln + a / ln))).astype(f)}

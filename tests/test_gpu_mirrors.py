@@ -173,3 +173,32 @@ def test_join_adjacency_drives_the_merge_loop(cuda):
     got = merge_graph(T(ps), T(cnt), T(area), T(per), T(jk), T(blen.view(np.int32)), 0.5)
     assert np.array_equal(got.root.cpu().numpy(), want["root"]) and got.rounds == want["rounds"] and got.merges == want["merges"]
     assert np.array_equal(got.edge_keys.cpu().numpy().view(np.uint64), want["keys"])
+
+
+@pytest.mark.parametrize("shape", [(96, 128, 40), (257, 301, 150), (1030, 777, 2000)])
+def test_designed_attributes_on_the_device(cuda, shape):
+    """N2: RAG.attributes() from a device pass -- bounding boxes bit for bit against the oracle, the attributes against
+    oracle_np.shape_attributes / the pixels themselves (float32 of the same float64 expression)."""
+    import torch
+    from deepmerge_b200 import raster as rs
+    H, W, n = shape
+    sc = o.synth_scene(H, W, n, C=4, seed=H)
+    R = sc["n_regions"] + 3                                   # three ids without pixels
+    lab = sc["labels"].copy()
+    lab[5:9, 7:19] = -1                                       # a nodata hole
+    d_lab = torch.from_numpy(lab).cuda()
+    rag = rs.build_rag(d_lab, R, torch.from_numpy(sc["image"]).cuda(), bbox=True)
+    box = o.region_bbox(lab, R)
+    assert np.array_equal(rag.bbox.cpu().numpy(), box)
+    assert np.array_equal(rs.region_bbox(d_lab, R).cpu().numpy(), box)
+    area, perim = o.build_rag(lab, R)[2:4]
+    want = o.shape_attributes(area, perim, box)
+    a = {k: v.cpu().numpy() for k, v in rag.attributes().items()}
+    for k, v in want.items():
+        np.testing.assert_allclose(a[k], v, rtol=1e-6, equal_nan=True, err_msg=k)
+    assert np.isnan(a["len"][-3:]).all() and np.array_equal(a["area"], area.astype(np.float32))
+    r = int(np.argmax(area))
+    ys, xs = np.nonzero(lab == r)
+    assert a["len"][r] == max(np.ptp(xs), np.ptp(ys)) + 1 and a["width"][r] == min(np.ptp(xs), np.ptp(ys)) + 1
+    with pytest.raises(ValueError):
+        rs.region_bbox(d_lab, R - 10)

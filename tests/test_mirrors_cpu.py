@@ -152,6 +152,17 @@ def test_rag_attributes_from_the_pooled_statistics():
             np.testing.assert_allclose(a["bright"][r].item(), px.mean(axis=0).mean(), rtol=1e-6)
         else:
             assert torch.isnan(a["mean"][r]).all()
+    rag.bbox = torch.from_numpy(o.region_bbox(sc["labels"], R))
+    a = rag.attributes()
+    want = o.shape_attributes(area, perim, rag.bbox.numpy())
+    for k, v in want.items():
+        np.testing.assert_allclose(a[k].numpy(), v, rtol=1e-6, equal_nan=True, err_msg=k)
+    for r in range(0, R, 7):
+        ys, xs = np.nonzero(sc["labels"] == r)
+        if len(ys):
+            w, h = np.ptp(xs) + 1, np.ptp(ys) + 1
+            assert a["len"][r].item() == max(w, h) and a["width"][r].item() == min(w, h)
+            np.testing.assert_allclose(a["compact"][r].item(), w * h / len(ys), rtol=1e-6)
 
 
 def test_point_patches_grouping_logic(monkeypatch):
