@@ -155,8 +155,9 @@ __global__ void collect_members_kernel(const int32_t* __restrict__ parent, uint8
 
 // list sorted by (root, member).  The warp that lands on the head of a root's run adds the
 // members' sums into the root's sum one after another (ascending member id): a fixed fp32
-// summation order, so results do not depend on scheduling.  Each lane keeps up to 4 feature
-// columns in registers and 4 member rows of loads are in flight; the adds stay in order.
+// summation order, so results do not depend on scheduling.  The run is read 32 entries at a time
+// (one entry per lane: the run's end is a ballot, the member ids travel by shuffle), each lane keeps
+// up to 4 feature columns in registers and 8 member rows of loads are in flight; the adds stay in order.
 __global__ void __launch_bounds__(256) merge_sums_kernel(const uint64_t* __restrict__ list,
                                                          const int64_t* __restrict__ n_dev, float* __restrict__ sum,
                                                          int D) {
@@ -167,31 +168,37 @@ __global__ void __launch_bounds__(256) merge_sums_kernel(const uint64_t* __restr
     for (int64_t i = warp0; i < n; i += nwarps) {
         const int root = key_lo(list[i]);
         if (i > 0 && key_lo(list[i - 1]) == root) continue;
-        int64_t end = i + 1;                                   // run of this root: [i, end)
-        while (end < n && key_lo(list[end]) == root) ++end;
         for (int d0 = 0; d0 < D; d0 += 128) {
             float acc[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) acc[k] = (d0 + lane + 32 * k < D) ? sum[(int64_t)root * D + d0 + lane + 32 * k] : 0.f;
             int64_t j = i;
-            for (; j + 4 <= end; j += 4) {
-                float v[4][4];
+            while (true) {
+                const int64_t idx = j + lane;
+                const uint64_t kk = idx < n ? list[idx] : 0ull;
+                const unsigned same = __ballot_sync(0xffffffffu, idx < n && key_lo(kk) == root);
+                const int len = same == 0xffffffffu ? 32 : __ffs(~same) - 1;    // entries of this run among the 32
+                const int member = key_hi(kk);
+                for (int u0 = 0; u0 < len; u0 += 8) {
+                    float v[8][4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float* row = sum + (int64_t)key_hi(list[j + u]) * D + d0;
+                    for (int u = 0; u < 8; ++u) {
+                        if (u0 + u < len) {                                    // (len is the same in every lane)
+                            const float* row = sum + (int64_t)__shfl_sync(0xffffffffu, member, u0 + u) * D + d0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) v[u][k] = (d0 + lane + 32 * k < D) ? row[lane + 32 * k] : 0.f;
+                            for (int k = 0; k < 4; ++k) v[u][k] = (d0 + lane + 32 * k < D) ? row[lane + 32 * k] : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (u0 + u < len) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) acc[k] += v[u][k];
+                        }
+                    }
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc[k] += v[u][k];
-            }
-            for (; j < end; ++j) {
-                const float* row = sum + (int64_t)key_hi(list[j]) * D + d0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (d0 + lane + 32 * k < D) acc[k] += row[lane + 32 * k];
+                j += len;
+                if (len < 32) break;
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -709,7 +716,7 @@ extern "C" int dm_merge_apply_masked(const int32_t* parent, uint8_t* alive, uint
                                                               (unsigned long long*)n_list, (unsigned long long*)n_merged,
                                                               root_mask);
     const int b = bits_for(R);
-    DM_TRY(prims::sort_pairs(list, nullptr, n_list, R, b, 2 * b, sws, s, prims::sort_fused_mode() >= 2));
+    DM_TRY(prims::sort_pairs(list, nullptr, n_list, R, b, 2 * b, sws, s, prims::sort_fused_mode() >= 2, R));
     DM_COUNT_LAUNCH(); merge::merge_sums_kernel<<<grid_for(R * 32), 256, 0, s>>>(list, n_list, sum, (int)D);
     DM_LAUNCH_CHECK();
     return DM_OK;
@@ -750,7 +757,7 @@ extern "C" int dm_edges_rekey(const int32_t* parent, uint64_t* keys, uint32_t* l
     const int b = bits_for(R + 1);
     int64_t* n_new = c.take<int64_t>(1);
     DM_TRY(prims::sort_unique(nk, perm, n_dev, capacity, b, 2 * b, sws, lens, scores, sentinel, ok, ol, scores ? os : nullptr,
-                              n_new, uws, keys, lens, scores, n_dev, s));
+                              n_new, uws, keys, lens, scores, n_dev, s, R));
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

@@ -57,35 +57,70 @@ __global__ void __launch_bounds__(256) pool_points_kernel(const int64_t* __restr
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < R; r += nwarps) {
-        const int64_t a = offsets[r], b = offsets[r + 1];
-        float acc[K];
+    // A region costs three dependent round trips (offsets -> point ids -> rows).  The warp therefore looks one region
+    // ahead: the next region's offsets are requested before this region's rows, and its point ids (one per lane) as
+    // soon as those offsets arrive, while the rows are still in flight.
+    int64_t r = warp0, a = 0, b = 0;
+    int my = 0;                                            // lane l holds the id of the region's point a + l
+    if (r < R) {
+        a = offsets[r];
+        b = offsets[r + 1];
+        my = a + lane < b ? ids[a + lane] : 0;
+    }
+    auto rows4 = [&](float (&v)[4][K], int id_lane, int u0, int n) {   // rows u0 .. u0+3 of the (<= 32) ids held by the lanes
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = 0.f;
-        int64_t j = a;
-        for (; j + 4 <= b; j += 4) {   // 4 rows of loads in flight; the adds stay in order
-            float v[4][K];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float* row = feats + (int64_t)ids[j + u] * ld + d_base;
+        for (int u = 0; u < 4; ++u) {
+            if (u0 + u < n) {                              // (n is the same in every lane)
+                const float* row = feats + (int64_t)__shfl_sync(0xffffffffu, id_lane, u0 + u) * ld + d_base;
 #pragma unroll
                 for (int k = 0; k < K; ++k) v[u][k] = (d_base + lane + 32 * k < D) ? row[lane + 32 * k] : 0.f;
             }
+        }
+    };
+    auto add4 = [&](float (&acc)[K], const float (&v)[4][K], int u0, int n) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u) {
+            if (u0 + u < n) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) acc[k] += v[u][k];
+            }
         }
-        for (; j < b; ++j) {
-            const float* row = feats + (int64_t)ids[j] * ld + d_base;
+    };
+    while (r < R) {
+        const int64_t rn = r + nwarps;
+        int64_t an = 0, bn = 0;
+        if (rn < R) {
+            an = offsets[rn];
+            bn = offsets[rn + 1];
+        }
+        float acc[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k)
-                if (d_base + lane + 32 * k < D) acc[k] += row[lane + 32 * k];
+        for (int k = 0; k < K; ++k) acc[k] = 0.f;
+        const int n0 = (int)imin64(b - a, 32);
+        float v[4][K];
+        rows4(v, my, 0, n0);
+        const int myn = (rn < R && an + lane < bn) ? ids[an + lane] : 0;    // waits for an / bn beside the rows above
+        add4(acc, v, 0, n0);
+        for (int u0 = 4; u0 < n0; u0 += 4) {
+            rows4(v, my, u0, n0);
+            add4(acc, v, u0, n0);
+        }
+        for (int64_t j = a + 32; j < b; j += 32) {         // more than 32 points: further chunks of ids
+            const int n1 = (int)imin64(b - j, 32);
+            const int more = j + lane < b ? ids[j + lane] : 0;
+            for (int u0 = 0; u0 < n1; u0 += 4) {
+                rows4(v, more, u0, n1);
+                add4(acc, v, u0, n1);
+            }
         }
 #pragma unroll
         for (int k = 0; k < K; ++k)
             if (d_base + lane + 32 * k < D) sum[r * D + d_base + lane + 32 * k] = acc[k];
         if (lane == 0 && d_base == 0) cnt[r] = (int32_t)(b - a);
+        r = rn;
+        a = an;
+        b = bn;
+        my = myn;
     }
 }
 
@@ -104,10 +139,19 @@ __global__ void __launch_bounds__(256) region_mean_kernel(const float* __restric
         const int n = cnt[r];
         const float c = n > 0 ? (float)n : __int_as_float(0x7fc00000);
         float n2 = 0.f;
-        for (int d = lane; d < D; d += 32) {
-            const float v = n > 0 ? __fdiv_rn(sum[r * D + d], c) : c;
-            mean[r * D + d] = v;
-            n2 = __fmaf_rn(v, v, n2);
+        for (int d0 = 0; d0 < D; d0 += 128) {          // four loads in flight per lane; same order of the norm's terms
+            float x[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = (n > 0 && d0 + 32 * k + lane < D) ? sum[r * D + d0 + 32 * k + lane] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int d = d0 + 32 * k + lane;
+                if (d < D) {
+                    const float v = n > 0 ? __fdiv_rn(x[k], c) : c;
+                    mean[r * D + d] = v;
+                    n2 = __fmaf_rn(v, v, n2);
+                }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
@@ -349,7 +393,12 @@ extern "C" int dm_csr_build(const int32_t* rop, int64_t n, int64_t R, int64_t* o
     DM_COUNT_LAUNCH(); pool::csr_keys_kernel<<<g, 256, 0, s>>>(rop, n, R, keys, vals, n_dev);
     // stable sort by region only (input is in ascending point id): low bits_for(R+1) bits
     const int b = bits_for(R + 1);
-    DM_TRY(prims::sort_pairs(keys, vals, n_dev, n, b, b, sws, s, false));   // runs beside the raster pass
+    // bucket + rank in one cooperative launch, offsets and point ids included ...
+    const int rc = prims::sort_pairs(keys, vals, n_dev, n, b, b, sws, s, true, R + 1, offsets, point_ids);
+    if (rc == DM_OK) return DM_OK;
+    if (rc != DM_ERR_UNSUPPORTED) return rc;
+    // ... or radix passes, one launch per phase, and a binary search per region
+    DM_TRY(prims::sort_pairs(keys, vals, n_dev, n, b, b, sws, s, false));
     DM_COUNT_LAUNCH(); pool::csr_offsets_kernel<<<pool::grid_for((n > R ? n : R) + 1, 256, 8), 256, 0, s>>>(keys, vals, n, R, offsets, point_ids);
     DM_LAUNCH_CHECK();
     return DM_OK;

@@ -25,8 +25,13 @@ size_t sort_ws_bytes(int64_t cap);
 // key_bits = 2*id_bits sorts by (hi, lo); key_bits = id_bits sorts by lo only.  vals may be null.
 // allow_fused: the whole sort may run as ONE cooperative launch (persistent blocks + grid barriers); callers that
 // sort beside a kernel filling every SM (the pooling chain beside the raster pass) pass false.
+// n_ids > 0 (with key_bits = id_bits or 2 id_bits): the primary half of every key is an id < n_ids, and the sort may
+// run as bucket + rank in one cooperative launch (bucket_sort_fused in prims.cu).  csr_offsets / csr_ids (need
+// n_ids > 0 and a cooperative launch; DM_ERR_UNSUPPORTED otherwise, the caller then takes its own path): also
+// offsets[id] = first sorted position of primary id `id`, for id < n_ids, and the sorted values as int32.
 int sort_pairs(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t cap, int id_bits, int key_bits,
-               void* ws, cudaStream_t s, bool allow_fused = true);
+               void* ws, cudaStream_t s, bool allow_fused = true, int64_t n_ids = 0, int64_t* csr_offsets = nullptr,
+               int32_t* csr_ids = nullptr);
 bool sort_fused_available();
 int sort_fused_mode();   // DM_SORT_FUSED: 0 off, 1 edge sorts, 2 (default) also the member sort of dm_merge_apply
 
@@ -45,7 +50,10 @@ int unique_reduce(const uint64_t* keys, const uint32_t* perm, const uint32_t* le
 int sort_unique(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t cap, int id_bits, int key_bits, void* sort_ws,
                 const uint32_t* gather_lens, const float* gather_scores, uint64_t sentinel, uint64_t* out_keys,
                 uint32_t* out_lens, float* out_scores, int64_t* n_out_dev, void* unique_ws, uint64_t* back_keys,
-                uint32_t* back_lens, float* back_scores, int64_t* back_n, cudaStream_t s);
+                uint32_t* back_lens, float* back_scores, int64_t* back_n, cudaStream_t s, int64_t n_ids = 0);
+// n_ids > 0: both halves of every key that is not the sentinel are ids < n_ids and only the reduced list is wanted
+// (keys / vals keep their contents): the run reduction may then go through a hash table + per-id buckets instead of
+// sorting the raw entries (edge_unique_hashed in prims.cu; DM_EDGE_HASH=0 switches it off).
 
 // ---- device helpers -------------------------------------------------------------------
 

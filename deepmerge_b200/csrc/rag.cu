@@ -156,7 +156,7 @@ extern "C" int dm_rag_finish(uint64_t* edge_keys, uint32_t* boundary_len, int64_
         n_raw = w.n_raw;
     }
     DM_TRY(prims::sort_unique(w.raw_keys, w.raw_cnt, n_raw, capacity, b, 2 * b, w.sws, nullptr, nullptr, ~0ull, edge_keys,
-                              boundary_len, nullptr, counts, w.uws, nullptr, nullptr, nullptr, nullptr, s));
+                              boundary_len, nullptr, counts, w.uws, nullptr, nullptr, nullptr, nullptr, s, n_regions));
     DM_LAUNCH_CHECK();
     return DM_OK;
 }
@@ -247,7 +247,7 @@ extern "C" int dm_edges_sort_unique(uint64_t* keys, uint32_t* lens, const int64_
     void* uws = c.take<char>(prims::unique_ws_bytes(capacity));
     const int b = bits_for(n_regions);
     DM_TRY(prims::sort_unique(keys, lens, n_in, capacity, b, 2 * b, sws, nullptr, nullptr, ~0ull, ok, ol, nullptr, n_new, uws,
-                              keys, lens, nullptr, n_out, s));
+                              keys, lens, nullptr, n_out, s, n_regions));
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

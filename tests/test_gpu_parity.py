@@ -49,9 +49,12 @@ def test_sort_edges(cuda, n, R):
     assert np.array_equal(v[:n].cpu().numpy().view(np.uint32), vals[order])      # stable
 
 
-@pytest.mark.parametrize("n,R", [(0, 10), (1, 2), (2048, 3), (5000, 40), (300000, 700), (2500000, 2500)])
+@pytest.mark.parametrize("n,R", [(0, 10), (1, 2), (2048, 3), (5000, 40), (300000, 700), (2500000, 2500), (20000, 100),
+                                 (600000, 200000), (3000000, 6000)])
 def test_edges_sort_unique(cuda, n, R):
-    """Sort + run reduction (one cooperative launch when available): unique keys ascending, lengths summed."""
+    """Run reduction of an edge list (one cooperative launch when available): unique keys ascending, lengths summed.
+    The cases cover the hashed path with small buckets, with hub buckets (R = 100, 700), and its fall-back to the radix
+    sort (more hubs than the hub list holds: R = 2500; a bucket above the hub limit: R = 6000)."""
     import torch
     from deepmerge_b200._lib import lib
     L = lib()
@@ -170,6 +173,25 @@ def test_rag_nodata_and_every_pixel_its_own_region(cuda):
     check_rag(cuda, L, 50, img)
     L2 = np.arange(H * W, dtype=np.int32).reshape(H, W)           # E = 2HW - H - W, tables saturate
     check_rag(cuda, L2, H * W, img, capacity=2 * H * W)
+
+
+@pytest.mark.parametrize("islands", [300, 5000])
+@pytest.mark.parametrize("background_first", [True, False])
+def test_rag_hub_region(cuda, islands, background_first):
+    """One background region touching hundreds / thousands of islands: a bucket of the hashed run reduction that is
+    ranked by a whole block (300) or sends the call down the radix path (5000, when the background has the lowest id)."""
+    side = int(np.ceil(np.sqrt(islands)))
+    H = W = 4 * side + 3
+    bg = 0 if background_first else islands
+    L = np.full((H, W), bg, np.int32)
+    k = 0
+    for i in range(side):
+        for j in range(side):
+            if k < islands:
+                L[4 * i + 2:4 * i + 4, 4 * j + 2:4 * j + 5] = k + (1 if background_first else 0)
+                k += 1
+    rag = check_rag(cuda, L, islands + 1)
+    assert rag.n_edges >= islands
 
 
 def test_rag_capacity_overflow_is_reported_and_retried(cuda):
