@@ -12,7 +12,8 @@ import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "deepmerge_b200.h")
-LIB_PATH = os.path.join(HERE, "libdeepmerge_b200.so")
+# DM_LIB_PATH: another build of the same ABI (A/B timing of two library versions on one box, tools/ab_build.sh)
+LIB_PATH = os.environ.get("DM_LIB_PATH") or os.path.join(HERE, "libdeepmerge_b200.so")
 SYNTH_HEADER = os.path.join(os.path.dirname(HERE), "include", "deepmerge_b200_synth.h")
 SYNTH_LIB_PATH = os.path.join(HERE, "libdeepmerge_b200_synth.so")
 

@@ -445,6 +445,41 @@ __global__ void __launch_bounds__(256) peer_put_kernel(const unsigned char* __re
     }
 }
 
+// Two-shot all-reduce of an int32 array that lives at the same offset of every rank's symmetric buffer, over NVLink peer
+// memory: rank g reduces slice g of all ranks' arrays (peer loads) and stores the result into slice g of EVERY rank's
+// array (peer stores), in place.  A barrier over all ranks before this kernel (every rank's array is complete) and one
+// after it (every slice has landed) are the caller's.  Slices are whole 16-byte units; op 0 = sum, 1 = min.
+__device__ __forceinline__ int4 ld_peer_v4(const int4* p) {
+    int4 v;
+    asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__global__ void __launch_bounds__(256) peer_allreduce_i32_kernel(const long long* __restrict__ peer_bases, int world, int rank,
+                                                                 int64_t offset_bytes, int64_t n4, int op) {
+    const int64_t per = (n4 + world - 1) / world;
+    const int64_t lo = (int64_t)rank * per, hi = imin64(n4, lo + per);
+    for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+        int4 acc = op ? make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff) : make_int4(0, 0, 0, 0);
+        for (int p0 = 0; p0 < world; p0 += 8) {            // up to 8 peer loads in flight
+            int4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (p0 + j < world) v[j] = ld_peer_v4((const int4*)((const unsigned char*)peer_bases[p0 + j] + offset_bytes) + i);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (p0 + j < world) {
+                    if (op) {
+                        acc.x = min(acc.x, v[j].x); acc.y = min(acc.y, v[j].y); acc.z = min(acc.z, v[j].z); acc.w = min(acc.w, v[j].w);
+                    } else {
+                        acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w;
+                    }
+                }
+            }
+        }
+        for (int p = 0; p < world; ++p) *((int4*)((unsigned char*)peer_bases[p] + offset_bytes) + i) = acc;
+    }
+}
+
 // The flag words of one round of the distributed loop, filled from the engine's counters in ONE launch (they were a
 // dozen elementwise launches from the host): flags[0] = edges selected; first round: [3] tile edge-list overflow, [4] bad
 // label, [5] internal error, [6] raw entries needed; then flags -> the header of the frontier slot.
@@ -541,6 +576,20 @@ extern "C" int dm_peer_put_slot(const void* slot, const int64_t* peer_bases_dev,
     DM_COUNT_LAUNCH(); merge::peer_put_kernel<<<grid_for(units), 256, 0, S(stream)>>>(
         (const unsigned char*)slot, (const long long*)peer_bases_dev, (int)world, (int)rank, slot_bytes, header_bytes / 16, seg0_offset,
         seg0_elem_bytes, seg1_offset, seg1_elem_bytes, capacity);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_peer_allreduce_i32(const void* peer_bases_dev, int64_t world, int64_t rank, int64_t offset_bytes, int64_t n,
+                                     int op, dm_stream_t stream) {
+    if (world < 1 || world > 64 || rank < 0 || rank >= world || offset_bytes < 0 || (offset_bytes & 15) || n < 0 || (n & 3) ||
+        (op != 0 && op != 1))
+        return DM_ERR_BAD_ARG;
+    if (n == 0) return DM_OK;
+    if (!peer_bases_dev) return DM_ERR_BAD_ARG;
+    const int64_t n4 = n / 4, per = ceil_div(n4, world);
+    DM_COUNT_LAUNCH(); merge::peer_allreduce_i32_kernel<<<grid_for(per), 256, 0, S(stream)>>>(
+        (const long long*)peer_bases_dev, (int)world, (int)rank, offset_bytes, n4, op);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

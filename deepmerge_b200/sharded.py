@@ -118,6 +118,33 @@ class PeerSlots:
         return t.view(self.world, self.slot_bytes)
 
 
+class PeerArray:
+    """An int32 array in torch symmetric memory (every rank's copy is mapped into every process) with an in-place
+    all-reduce made of this library's kernel over NVLink peer loads / stores (dm_peer_allreduce_i32: rank g reduces
+    slice g of all copies and stores it into all of them) between two signal-pad barriers -- no NCCL call."""
+
+    def __init__(self, dist, group, n, device):
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        name = (group if group is not None else dist.group.WORLD).group_name
+        self.n_pad = n + (-n) % 4
+        self.buf = symm.empty(self.n_pad, dtype=torch.int32, device=device)
+        self.hdl = symm.rendezvous(self.buf, name)
+        self.bases = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        self.buf.zero_()
+        self.tensor = self.buf[:n]
+        torch.cuda.synchronize(device)
+        self.hdl.barrier()
+
+    def all_reduce(self, L, op, stream):
+        """op 0 = sum, 1 = min; in place, on the current stream."""
+        from .raster import _p
+        self.hdl.barrier()                 # every rank's copy is complete (its producers precede the barrier in stream order)
+        L.check(L.dm_peer_allreduce_i32(_p(self.bases), self.world, self.rank, 0, self.n_pad, op, stream),
+                "dm_peer_allreduce_i32")
+        self.hdl.barrier()                 # every slice has landed everywhere
+
+
 def _peer_exchange_possible(dist):
     """Symmetric memory needs the real torch.distributed over NCCL (one process per GPU); DM_SHARD_PEER=0 forces the
     collective path."""
@@ -196,13 +223,19 @@ class ShardedMergeEngine:
         self.fslot = z(self.fslot_bytes, dt=torch.uint8)
         self.fslot_flags = self.fslot[16:80].view(torch.int64)
         self.flags = z(8, dt=torch.int64)
-        self.peer_rows = self.peer_pairs = None
+        self.peer_rows = self.peer_pairs = self.peer_mask_cnt = self.peer_parent = None
         if _peer_exchange_possible(self.dist):
             try:
                 self.peer_rows = PeerSlots(self.dist, self.group, self.slot_bytes, dev)
                 self.peer_pairs = PeerSlots(self.dist, self.group, self.fslot_bytes, dev)
+                if os.environ.get("DM_SHARD_PEER_REDUCE", "1") != "0":
+                    # the two replicated R-sized arrays live in symmetric memory: their all-reduces are peer kernels
+                    pm, pp = PeerArray(self.dist, self.group, 2 * R, dev), PeerArray(self.dist, self.group, R, dev)
+                    self.peer_mask_cnt, self.peer_parent = pm, pp
+                    self.mask_cnt, self.mask = pm.tensor, pm.tensor[:R]
+                    e.parent = pp.tensor
             except Exception as ex:                                # no NVLink peer access / symmetric memory on this box
-                self.peer_rows = self.peer_pairs = None
+                self.peer_rows = self.peer_pairs = self.peer_mask_cnt = self.peer_parent = None
                 self.peer_error = repr(ex)
         self.host_fflags = torch.zeros((self.world, 10), dtype=torch.int64).pin_memory()
         self.hdr_dev = z(self.world, 80, dt=torch.uint8)
@@ -280,7 +313,10 @@ class ShardedMergeEngine:
             cur.wait_stream(e.side)
             L.check(L.dm_shard_seen(_p(e.area), _p(self.seen), _p(e.cnt), self.rank, R, _p(self.mask_cnt), _p(self.cnt_local), s),
                     "dm_shard_seen")
-            dist.all_reduce(self.mask_cnt, op=SUM, group=grp)       # masks: distinct bits, the sum is the OR; counts add up
+            if self.peer_mask_cnt is not None:                      # masks: distinct bits, the sum is the OR; counts add up
+                self.peer_mask_cnt.all_reduce(L, 0, s)
+            else:
+                dist.all_reduce(self.mask_cnt, op=SUM, group=grp)
             self.flags.zero_()
             L.check(L.dm_shard_frontier(_p(self.mask_cnt), _p(self.cnt_local), R, _p(e.cnt), _p(self.send), s), "dm_shard_frontier")
             self._exchange_rows(self.send, add=True)
@@ -333,7 +369,10 @@ class ShardedMergeEngine:
                 L.check(L.dm_uf_union_slots(_p(e.parent), _p(fg), self.world, self.fslot_bytes, self.row_cap, R, s),
                         "dm_uf_union_slots")
                 L.check(L.dm_uf_compress(_p(e.parent), R, s), "dm_uf_compress")
-                dist.all_reduce(e.parent, op=MIN, group=grp)       # fills in the regions this rank does not see
+                if self.peer_parent is not None:                   # fills in the regions this rank does not see
+                    self.peer_parent.all_reduce(L, 1, s)
+                else:
+                    dist.all_reduce(e.parent, op=MIN, group=grp)
                 # rows of components that grew across a tile border go to every rank that now sees them
                 self.mask_old.copy_(self.mask)
                 L.check(L.dm_shard_propagate(_p(e.parent), _p(e.alive), _p(self.mask), _p(self.grew), R, s), "dm_shard_propagate")

@@ -319,6 +319,15 @@ int dm_uf_union_slots(int32_t* parent, const void* slots, int64_t n_slots, int64
  * the caller's communicator stays opaque to the library).  Only the used part travels.  The caller runs a barrier over
  * the ranks after it (and alternates two buffers, so that a buffer is rewritten only after every rank has passed the
  * barrier that follows its last read).  All offsets / sizes in bytes, multiples of 16 where they are addresses. */
+/* Two-shot all-reduce of an int32 array over NVLink peer memory (the replicated per-region state of the sharded merge
+ * loop: visibility masks + point counts (sum), the parent array (min); replaces torch.distributed.all_reduce there).
+ * The array sits at offset_bytes of every rank's symmetric buffer (peer_bases_dev[p] = rank p's buffer mapped into this
+ * process, as for dm_peer_put_slot); n int32 values, n a multiple of 4, offset a multiple of 16.  Rank g reduces slice g of
+ * all ranks' arrays and stores it into every rank's array.  The caller brackets the call with barriers over all ranks
+ * (before: every rank's array is complete; after: every slice has landed).  op 0 = sum, 1 = min. */
+int dm_peer_allreduce_i32(const void* peer_bases_dev, int64_t world, int64_t rank, int64_t offset_bytes, int64_t n, int op,
+                          dm_stream_t stream);
+
 /* host-side glue of the distributed loop as single launches: dm_shard_round_flags fills the eight flag words of a round
  * from the engine's counters (flags[0] = counts[4] edges selected; first round also [3] = counts[2] != 0 overflow, [4] =
  * counts[3] == 1 bad label, [6] = counts[1] raw entries needed; every round [5] |= counts[3] > 1 internal error) and copies them into
