@@ -52,10 +52,13 @@ __global__ void csr_offsets_kernel(const uint64_t* __restrict__ keys, const uint
 template <int K>
 __global__ void __launch_bounds__(256) pool_points_kernel(const int64_t* __restrict__ offsets,
                                                           const int32_t* __restrict__ ids, const float* __restrict__ feats,
-                                                          int64_t ld, int64_t R, int D, int d_base, float* __restrict__ sum,
-                                                          int32_t* __restrict__ cnt) {
+                                                          int64_t ld, int64_t R_all, int D, int d_base, float* __restrict__ sum,
+                                                          int32_t* __restrict__ cnt, const int64_t* __restrict__ range) {
     const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // range (row tiles of a sharded scene: ids are global, the tile's points fall into a small id interval): only
+    // regions [range[0], range[1]] are visited; rows and counts outside are the caller's
+    const int64_t r_first = range ? imax64(range[0], 0) : 0, R = range ? imin64(range[1] + 1, R_all) : R_all;
+    const int64_t warp0 = r_first + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     // A region costs three dependent round trips (offsets -> point ids -> rows).  The warp therefore looks one region
     // ahead: the next region's offsets are requested before this region's rows, and its point ids (one per lane) as
@@ -406,22 +409,69 @@ extern "C" int dm_csr_build(const int32_t* rop, int64_t n, int64_t R, int64_t* o
 
 template <int K>
 static void launch_pool_points(const int64_t* offsets, const int32_t* ids, const float* feats, int64_t ld, int64_t R,
-                               int D, int d_base, float* sum, int32_t* cnt, cudaStream_t s) {
-    DM_COUNT_LAUNCH(); pool::pool_points_kernel<K><<<pool::grid_for(R * 32, 256, 8), 256, 0, s>>>(offsets, ids, feats, ld, R, D, d_base, sum, cnt);
+                               int D, int d_base, float* sum, int32_t* cnt, const int64_t* range, cudaStream_t s) {
+    DM_COUNT_LAUNCH(); pool::pool_points_kernel<K><<<pool::grid_for(R * 32, 256, 8), 256, 0, s>>>(offsets, ids, feats, ld, R, D, d_base, sum, cnt, range);
 }
 
-extern "C" int dm_pool_points_csr(const int64_t* offsets, const int32_t* ids, const float* feats, int64_t ld, int64_t R,
-                                  int64_t D, float* sum, int32_t* cnt, dm_stream_t stream) {
+extern "C" int dm_pool_points_csr_tile(const int64_t* offsets, const int32_t* ids, const float* feats, int64_t ld, int64_t R,
+                                       int64_t D, float* sum, int32_t* cnt, const int64_t* region_range, dm_stream_t stream) {
     if (R < 0 || D <= 0 || ld < D || D > (1 << 20)) return DM_ERR_BAD_ARG;
     if (R == 0) return DM_OK;
     if (!offsets || !sum || !cnt) return DM_ERR_BAD_ARG;
     cudaStream_t s = S(stream);
+    if (region_range) DM_CUDA(cudaMemsetAsync(cnt, 0, (size_t)R * sizeof(int32_t), s));   // no points outside the range
     for (int d0 = 0; d0 < D; d0 += 128) {
         const int rem = (int)D - d0;
-        if (rem > 96) launch_pool_points<4>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, s);
-        else if (rem > 64) launch_pool_points<3>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, s);
-        else if (rem > 32) launch_pool_points<2>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, s);
-        else launch_pool_points<1>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, s);
+        if (rem > 96) launch_pool_points<4>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, region_range, s);
+        else if (rem > 64) launch_pool_points<3>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, region_range, s);
+        else if (rem > 32) launch_pool_points<2>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, region_range, s);
+        else launch_pool_points<1>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, region_range, s);
+    }
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_points_csr(const int64_t* offsets, const int32_t* ids, const float* feats, int64_t ld, int64_t R,
+                                  int64_t D, float* sum, int32_t* cnt, dm_stream_t stream) {
+    return dm_pool_points_csr_tile(offsets, ids, feats, ld, R, D, sum, cnt, nullptr, stream);
+}
+
+// [first, last] region id that has a point (first > last: none); the argument of dm_pool_points_csr_tile
+namespace dm { namespace pool {
+__global__ void id_range_kernel(const int32_t* __restrict__ rop, int64_t n, int64_t R, long long* __restrict__ range) {
+    long long lo = 0x7fffffffffffffffll, hi = -1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = rop[i];
+        if (r >= 0 && r < R) {
+            lo = lo < r ? lo : r;
+            hi = hi > r ? hi : r;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = lo < l2 ? lo : l2;
+        hi = hi > h2 ? hi : h2;
+    }
+    if ((threadIdx.x & 31) == 0 && hi >= 0) {
+        atomicMin(range, lo);
+        atomicMax(range + 1, hi);
+    }
+}
+__global__ void id_range_init_kernel(long long* range) {
+    range[0] = 0x7fffffffffffffffll;
+    range[1] = -1;
+}
+}}  // namespace dm::pool
+
+extern "C" int dm_points_id_range(const int32_t* region_of_point, int64_t n_points, int64_t n_regions, int64_t* range,
+                                  dm_stream_t stream) {
+    if (n_points < 0 || n_regions < 0 || !range) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    DM_COUNT_LAUNCH(); pool::id_range_init_kernel<<<1, 1, 0, s>>>((long long*)range);
+    if (n_points > 0) {
+        if (!region_of_point) return DM_ERR_BAD_ARG;
+        DM_COUNT_LAUNCH(); pool::id_range_kernel<<<pool::grid_for(n_points, 256, 4), 256, 0, s>>>(region_of_point, n_points, n_regions, (long long*)range);
     }
     DM_LAUNCH_CHECK();
     return DM_OK;

@@ -456,6 +456,7 @@ class MergeEngine:
         self.cap = default_edge_capacity(n_regions, H, W) if edge_capacity is None else int(edge_capacity)
         self.logits = None
         self._means_fresh = self._init_fresh = False     # run() prepares both beside the raster pass
+        self.pool_id_range, self.id_range = False, None  # a row tile's engine (sharded.py) pools only the id interval of its points
         self._alloc()
 
     def _alloc(self):
@@ -516,8 +517,14 @@ class MergeEngine:
             region_of_point = self.rop
         L.check(L.dm_csr_build(_p(region_of_point), N, self.R, _p(self.offsets), _p(self.pids), _p(self.ws_pool),
                                self.ws_pool_bytes, s), "dm_csr_build")
-        L.check(L.dm_pool_points_csr(_p(self.offsets), _p(self.pids), _p(feats), feats.stride(0), self.R, self.D,
-                                     _p(self.sum), _p(self.cnt), s), "dm_pool_points_csr")
+        rng = None
+        if self.pool_id_range:          # a row tile's engine: only the id interval that holds the tile's points is visited
+            if self.id_range is None:
+                self.id_range = torch.zeros(2, dtype=_I64, device=self.dev)
+            L.check(L.dm_points_id_range(_p(region_of_point), N, self.R, _p(self.id_range), s), "dm_points_id_range")
+            rng = self.id_range
+        L.check(L.dm_pool_points_csr_tile(_p(self.offsets), _p(self.pids), _p(feats), feats.stride(0), self.R, self.D,
+                                          _p(self.sum), _p(self.cnt), _p(rng), s), "dm_pool_points_csr_tile")
 
     def _mean_all(self):
         L = self.L

@@ -237,6 +237,7 @@ class ShardedMergeEngine:
             except Exception as ex:                                # no NVLink peer access / symmetric memory on this box
                 self.peer_rows = self.peer_pairs = self.peer_mask_cnt = self.peer_parent = None
                 self.peer_error = repr(ex)
+        e.sum.zero_()                                              # rows the pooling pass never writes start as zeros
         self.host_fflags = torch.zeros((self.world, 10), dtype=torch.int64).pin_memory()
         self.hdr_dev = z(self.world, 80, dt=torch.uint8)
         self.host_flags = torch.zeros(8, dtype=torch.int64).pin_memory()
@@ -295,6 +296,11 @@ class ShardedMergeEngine:
         if not hasattr(self, "mask"):
             self._alloc_dist()
         MIN, MAX, SUM = dist.ReduceOp.MIN, dist.ReduceOp.MAX, dist.ReduceOp.SUM
+        # ids are global: most regions have no point in this tile.  Their sum rows are never read here (a row is read only
+        # for a region with points of its own, a received partial / shipped row, or a merge -- and a region without sample
+        # points never merges), so the pooling pass visits only the id interval that holds the tile's points instead of
+        # zero-filling R x D floats per step.
+        e.pool_id_range = True
         with torch.cuda.device(e.dev):
             s = _stream()
             n_edges = e.counts[0:1]
@@ -424,6 +430,7 @@ class ShardedMergeEngine:
         """labels_tile: int32 [rows_own (+1 halo), W]; ys_local_rel are rows relative to the tile."""
         from .raster import MergeResult, _p, _stream
         e, L, dist = self.eng, self.eng.L, self.dist
+        e.pool_id_range = False                         # the partial sums are all-reduced as whole arrays here
         with torch.cuda.device(e.dev):
             s = _stream()
             e._rag(labels_tile, image_tile, self.rows_own, self.rank == 0, self.rank == self.world - 1)

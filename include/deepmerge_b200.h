@@ -153,6 +153,15 @@ int dm_csr_build(const int32_t* region_of_point, int64_t n_points, int64_t n_reg
                  int32_t* point_ids, void* ws, size_t ws_bytes, dm_stream_t stream);
 int dm_pool_points_csr(const int64_t* offsets, const int32_t* point_ids, const float* feats, int64_t feat_ld,
                        int64_t n_regions, int64_t D, float* sum, int32_t* cnt, dm_stream_t stream);
+/* The same for the engine of one row tile of a sharded scene (ids are global, the tile's points fall into a small interval
+ * of them): region_range (device, int64[2] = first and last region id with a point, from dm_points_id_range; NULL = every
+ * region, which is dm_pool_points_csr) limits the pass to that interval: cnt becomes 0 for every region outside it and
+ * the sum rows outside are left untouched, so that the pass costs what the tile's own regions cost. */
+int dm_pool_points_csr_tile(const int64_t* offsets, const int32_t* point_ids, const float* feats, int64_t feat_ld,
+                            int64_t n_regions, int64_t D, float* sum, int32_t* cnt, const int64_t* region_range,
+                            dm_stream_t stream);
+int dm_points_id_range(const int32_t* region_of_point, int64_t n_points, int64_t n_regions, int64_t* range,
+                       dm_stream_t stream);
 /* mean[r] = sum[r] / cnt[r] (IEEE fp32 division), norm2[r] = sum_d mean[r,d]^2.  A region without sample points
  * (cnt[r] == 0) gets mean = norm2 = NaN -- what np.mean over no rows gives -- so that its edges score NaN
  * (dm_score_l2) / NaN logits (dm_score_mlp_bf16) and are never selected by dm_merge_select_*.
