@@ -32,7 +32,7 @@ def parse_header(path=HEADER):
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"//[^\n]*", "", src)
     protos = {}
-    for m in re.finditer(r"\b(int64_t|int|size_t|const char\s*\*)\s+(dm_\w+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(int64_t|int|size_t|void|const char\s*\*)\s+(dm_\w+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
         ret, name, args = m.group(1), m.group(2), m.group(3)
         restype = ctypes.c_char_p if "char" in ret else _SCALARS[ret]
         argtypes, argnames = [], []

@@ -37,6 +37,7 @@ extern "C" const char* dm_error_string(int code) {
 }
 
 extern "C" int64_t dm_launch_count(void) { return (int64_t)__atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
+extern "C" void dm_launch_count_add(int64_t n) { __atomic_add_fetch(&g_launch_count, (long long)n, __ATOMIC_RELAXED); }
 
 extern "C" int dm_last_cuda_error(void) { return g_last_cuda_error; }
 

@@ -9,6 +9,7 @@ signed view orders like the unsigned key).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -456,11 +457,14 @@ class MergeEngine:
         self.cap = default_edge_capacity(n_regions, H, W) if edge_capacity is None else int(edge_capacity)
         self.logits = None
         self._means_fresh = self._init_fresh = False     # run() prepares both beside the raster pass
+        self.use_graphs = os.environ.get("DM_GRAPHS", "1") != "0"
+        self._round_graphs = {}
         self.pool_id_range, self.id_range = False, None  # a row tile's engine (sharded.py) pools only the id interval of its points
         self._alloc()
 
     def _alloc(self):
         L, dev, R, D, C, N, cap = self.L, self.dev, self.R, self.D, self.C, self.N, self.cap
+        self._round_graphs = {}                           # captured round bodies point into the buffers below
         z = lambda *s, dt: torch.zeros(*s, dtype=dt, device=dev)
         e = lambda *s, dt: torch.empty(*s, dtype=dt, device=dev)
         with torch.cuda.device(dev):
@@ -635,14 +639,9 @@ class MergeEngine:
             self._mean_all()
         self._means_fresh = False
         self._score(mlp, None)
+        self._select(tau, mlp)
         rounds = merges = 0
         while True:
-            if mlp is None:
-                L.check(L.dm_merge_select_l2(_p(self.scores), float(tau), _p(n_edges), cap, _p(self.selected),
-                                             self.counts[4:5].data_ptr(), s), "dm_merge_select_l2")
-            else:
-                L.check(L.dm_merge_select_mlp(_p(self.logits), mlp.n_out, _p(n_edges), cap, _p(self.selected),
-                                              self.counts[4:5].data_ptr(), s), "dm_merge_select_mlp")
             c = self._read_counts()
             if rounds == 0:
                 if c[3] == 1:
@@ -657,23 +656,61 @@ class MergeEngine:
             if c[4] == 0 or rounds == max_rounds:
                 break
             rounds += 1
-            L.check(L.dm_uf_union(_p(self.parent), _p(self.keys), _p(self.selected), _p(n_edges), cap, s), "dm_uf_union")
-            L.check(L.dm_uf_compress(_p(self.parent), R, s), "dm_uf_compress")
-            # merged statistics (side stream) and edge re-keying (main stream) only share the parent array and integer
-            # atomics on the perimeter: two chains of small sort-dominated kernels that fill the GPU better together
-            cur = torch.cuda.current_stream(self.dev)
-            self.side.wait_stream(cur)
-            with torch.cuda.stream(self.side):
-                L.check(L.dm_merge_apply(_p(self.parent), _p(self.alive), _p(self.changed), _p(self.sum), _p(self.cnt),
-                                         _p(self.area), _p(self.perim), R, D, self.counts[5:6].data_ptr(), _p(self.ws_side),
-                                         self.ws_side_bytes, _stream()), "dm_merge_apply")
-            L.check(L.dm_edges_rekey(_p(self.parent), _p(self.keys), _p(self.blen), _p(self.scores), _p(n_edges), cap, R,
-                                     _p(self.perim), _p(self.ws), self.ws_bytes, s), "dm_edges_rekey")
-            cur.wait_stream(self.side)
-            L.check(L.dm_region_mean(_p(self.sum), _p(self.cnt), R, D, _p(self.mean), _p(self.norm2), _p(self.changed), s),
-                    "dm_region_mean")
-            self._score(mlp, self.changed)
+            self._round(tau, mlp)
         return rounds, merges
+
+    def _select(self, tau, mlp):
+        L, s, cap = self.L, _stream(), self.cap
+        n_edges = self.counts[0:1]
+        if mlp is None:
+            L.check(L.dm_merge_select_l2(_p(self.scores), float(tau), _p(n_edges), cap, _p(self.selected),
+                                         self.counts[4:5].data_ptr(), s), "dm_merge_select_l2")
+        else:
+            L.check(L.dm_merge_select_mlp(_p(self.logits), mlp.n_out, _p(n_edges), cap, _p(self.selected),
+                                          self.counts[4:5].data_ptr(), s), "dm_merge_select_mlp")
+
+    def _round_body(self, tau, mlp):
+        """One merge round between two read-backs: unions of the selected edges, merged statistics, re-keyed edge list,
+        means and scores of what changed, the next selection."""
+        L, s, R, D, cap = self.L, _stream(), self.R, self.D, self.cap
+        n_edges = self.counts[0:1]
+        L.check(L.dm_uf_union(_p(self.parent), _p(self.keys), _p(self.selected), _p(n_edges), cap, s), "dm_uf_union")
+        L.check(L.dm_uf_compress(_p(self.parent), R, s), "dm_uf_compress")
+        # merged statistics (side stream) and edge re-keying (main stream) only share the parent array and integer
+        # atomics on the perimeter: two chains of small kernels that fill the GPU better together
+        cur = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            L.check(L.dm_merge_apply(_p(self.parent), _p(self.alive), _p(self.changed), _p(self.sum), _p(self.cnt),
+                                     _p(self.area), _p(self.perim), R, D, self.counts[5:6].data_ptr(), _p(self.ws_side),
+                                     self.ws_side_bytes, _stream()), "dm_merge_apply")
+        L.check(L.dm_edges_rekey(_p(self.parent), _p(self.keys), _p(self.blen), _p(self.scores), _p(n_edges), cap, R,
+                                 _p(self.perim), _p(self.ws), self.ws_bytes, s), "dm_edges_rekey")
+        cur.wait_stream(self.side)
+        L.check(L.dm_region_mean(_p(self.sum), _p(self.cnt), R, D, _p(self.mean), _p(self.norm2), _p(self.changed), s),
+                "dm_region_mean")
+        self._score(mlp, self.changed)
+        self._select(tau, mlp)
+
+    def _round(self, tau, mlp):
+        """The round body as ONE CUDA graph launch (it only touches the engine's own buffers, so a captured body is valid
+        until they are re-allocated): a round is a dozen short kernels whose launch gaps otherwise show.  DM_GRAPHS=0:
+        plain launches."""
+        if not self.use_graphs:
+            return self._round_body(tau, mlp)
+        key = (float(tau), None if mlp is None else (id(mlp), mlp.blob.data_ptr()), self.cap)
+        ent = self._round_graphs.get(key)
+        if ent is None:
+            g = torch.cuda.CUDAGraph()
+            n0 = self.L.dm_launch_count()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._round_body(tau, mlp)
+            ent = (g, self.L.dm_launch_count() - n0)
+            if len(self._round_graphs) >= 8:
+                self._round_graphs.clear()
+            self._round_graphs[key] = ent
+        ent[0].replay()
+        self.L.dm_launch_count_add(ent[1])          # the library's counter saw the capture only
 
 
 class ScenePipeline:

@@ -107,11 +107,12 @@ class PeerSlots:
         self.bufs[0][1].barrier()
         self.k = 0
 
-    def exchange(self, L, slot, rank, header_bytes, seg0, seg1, capacity, stream):
-        """slot -> every rank's gathered buffer; returns this rank's gathered view [world, slot_bytes]."""
+    def exchange(self, L, slot, rank, header_bytes, seg0, seg1, capacity, stream, buf):
+        """slot -> every rank's gathered buffer `buf` (0 / 1); returns this rank's gathered view [world, slot_bytes].
+        The caller names the buffer (the loop's head uses 0, its round body 1), so that a captured round body replays
+        on the same addresses; two uses of one buffer are always separated by a barrier of the other exchange."""
         from .raster import _p
-        t, h, bases = self.bufs[self.k]
-        self.k ^= 1
+        t, h, bases = self.bufs[buf]
         L.check(L.dm_peer_put_slot(_p(slot), _p(bases), self.world, rank, self.slot_bytes, header_bytes, seg0[0], seg0[1],
                                    seg1[0], seg1[1], capacity, stream), "dm_peer_put_slot")
         h.barrier()
@@ -238,11 +239,12 @@ class ShardedMergeEngine:
                 self.peer_rows = self.peer_pairs = self.peer_mask_cnt = self.peer_parent = None
                 self.peer_error = repr(ex)
         e.sum.zero_()                                              # rows the pooling pass never writes start as zeros
+        self._dist_graphs, self._last_fg = {}, None
         self.host_fflags = torch.zeros((self.world, 10), dtype=torch.int64).pin_memory()
         self.hdr_dev = z(self.world, 80, dt=torch.uint8)
         self.host_flags = torch.zeros(8, dtype=torch.int64).pin_memory()
 
-    def _exchange_rows(self, flag, add):
+    def _exchange_rows(self, flag, add, buf):
         """Ship the embedding sums of the flagged regions to every rank: pack -> all_gather (fixed slots + device
         counts) -> unpack slot by slot in rank order (add: partial sums are accumulated in that order)."""
         from .raster import _p, _stream
@@ -251,7 +253,7 @@ class ShardedMergeEngine:
                                _p(self.slot_n), s), "dm_rows_pack")
         rc = self.row_cap
         if self.peer_rows is not None:     # one kernel storing the used part of the slot into every peer + a barrier
-            g = self.peer_rows.exchange(L, self.slot, self.rank, 16, (16, 4), (16 + 4 * rc, 4 * e.D), rc, s)
+            g = self.peer_rows.exchange(L, self.slot, self.rank, 16, (16, 4), (16 + 4 * rc, 4 * e.D), rc, s, buf)
         else:
             g = all_gather_slots(self.slot, dist, self.group).view(self.world, self.slot_bytes)
         # a slot that overflowed on ANY rank is seen by every rank in the gathered counts: all of them flag it
@@ -277,6 +279,91 @@ class ShardedMergeEngine:
         e.done.record()
         e.done.synchronize()
         return self.host_fflags.tolist(), e.host_counts.tolist()
+
+    def _pre_exchange(self, tau, mlp, do_unions, first_round, buf):
+        """Selection of the round, its local unions and the ONE exchange of the round -> gathered frontier slots.
+
+        The union-find of the round is prepared BEFORE anyone knows whether the round takes place: local unions, then the
+        frontier pairs (shared component, its local root).  The pairs of all ranks carry the whole cross-tile connectivity
+        -- no iteration, no convergence test -- and the round's flags ("edges selected", errors) travel in the same slot.
+        (Nothing selected anywhere: no unions, no pairs.)"""
+        from .raster import _p, _stream
+        e, L, s = self.eng, self.eng.L, _stream()
+        R, cap, n_edges = e.R, e.cap, e.counts[0:1]
+        e._select(tau, mlp)
+        if do_unions:
+            L.check(L.dm_uf_union(_p(e.parent), _p(e.keys), _p(e.selected), _p(n_edges), cap, s), "dm_uf_union")
+            L.check(L.dm_uf_compress(_p(e.parent), R, s), "dm_uf_compress")
+            L.check(L.dm_shard_frontier_pairs(_p(e.parent), _p(e.alive), _p(self.mask), self.rank, R, _p(self.fslot),
+                                              self.row_cap, s), "dm_shard_frontier_pairs")
+        else:
+            self.fslot[:16].zero_()
+        # the round's flags (edges selected; first round: this rank's tile-pass conditions) -> the slot header
+        L.check(L.dm_shard_round_flags(_p(e.counts), _p(self.flags), int(first_round), _p(self.fslot_flags), s),
+                "dm_shard_round_flags")
+        if self.peer_pairs is not None:                     # one kernel of NVLink peer stores + a barrier
+            return self.peer_pairs.exchange(L, self.fslot, self.rank, 80, (80, 8), (80, 0), self.row_cap, s, buf)
+        return all_gather_slots(self.fslot, self.dist, self.group).view(self.world, self.fslot_bytes)
+
+    def _dist_round_body(self, tau, mlp, do_unions, fg):
+        """One round between two read-backs: unions from everybody's frontier pairs, rows of the components that grew
+        across a tile border, merged statistics, re-keyed tile edge list, means / scores of what changed, and the next
+        round's selection + exchange."""
+        from .raster import _p, _stream
+        e, L, dist, grp, s = self.eng, self.eng.L, self.dist, self.group, _stream()
+        R, D, cap, n_edges = e.R, e.D, e.cap, e.counts[0:1]
+        L.check(L.dm_uf_union_slots(_p(e.parent), _p(fg), self.world, self.fslot_bytes, self.row_cap, R, s),
+                "dm_uf_union_slots")
+        L.check(L.dm_uf_compress(_p(e.parent), R, s), "dm_uf_compress")
+        if self.peer_parent is not None:                   # fills in the regions this rank does not see
+            self.peer_parent.all_reduce(L, 1, s)
+        else:
+            dist.all_reduce(e.parent, op=dist.ReduceOp.MIN, group=grp)
+        # rows of components that grew across a tile border go to every rank that now sees them
+        self.mask_old.copy_(self.mask)
+        L.check(L.dm_shard_propagate(_p(e.parent), _p(e.alive), _p(self.mask), _p(self.grew), R, s), "dm_shard_propagate")
+        L.check(L.dm_shard_plan(_p(e.parent), _p(e.alive), _p(self.mask_old), _p(self.mask), _p(self.grew), self.rank, R,
+                                _p(self.send), _p(self.seen_comp), s), "dm_shard_plan")
+        self._exchange_rows(self.send, add=False, buf=1)
+        cur = torch.cuda.current_stream(e.dev)
+        e.side.wait_stream(cur)                            # merged statistics beside the edge re-keying (as on one GPU)
+        with torch.cuda.stream(e.side):
+            L.check(L.dm_merge_apply_masked(_p(e.parent), _p(e.alive), _p(e.changed), _p(e.sum), _p(e.cnt), _p(e.area),
+                                            _p(e.perim), R, D, e.counts[5:6].data_ptr(), _p(self.seen_comp),
+                                            _p(e.ws_side), e.ws_side_bytes, _stream()), "dm_merge_apply_masked")
+        L.check(L.dm_edges_rekey(_p(e.parent), _p(e.keys), _p(e.blen), _p(e.scores), _p(n_edges), cap, R, _p(e.perim),
+                                 _p(e.ws), e.ws_bytes, s), "dm_edges_rekey")
+        cur.wait_stream(e.side)
+        L.check(L.dm_region_mean(_p(e.sum), _p(e.cnt), R, D, _p(e.mean), _p(e.norm2), _p(e.changed), s), "dm_region_mean")
+        e._score(mlp, e.changed)
+        return self._pre_exchange(tau, mlp, do_unions, False, 1)
+
+    def _dist_round(self, tau, mlp, do_unions):
+        """The round body as one CUDA graph launch when every exchange in it is a kernel of this library (peer stores /
+        peer all-reduce over symmetric memory + signal-pad barriers): ~35 short launches issued from Python otherwise."""
+        e = self.eng
+        graphs_ok = (e.use_graphs and self.peer_pairs is not None and self.peer_rows is not None and
+                     self.peer_parent is not None and os.environ.get("DM_SHARD_GRAPHS", "1") != "0")
+        # the body reads the gathered pairs of the previous exchange: buffer 0 after the head, buffer 1 after a body
+        src = self._last_fg
+        if not graphs_ok:
+            self._last_fg = self._dist_round_body(tau, mlp, do_unions, src)
+            return self._last_fg
+        key = (float(tau), None if mlp is None else (id(mlp), mlp.blob.data_ptr()), e.cap, bool(do_unions), src.data_ptr())
+        ent = self._dist_graphs.get(key)
+        if ent is None:
+            g = torch.cuda.CUDAGraph()
+            n0 = e.L.dm_launch_count()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                out = self._dist_round_body(tau, mlp, do_unions, src)
+            ent = (g, e.L.dm_launch_count() - n0, out)
+            if len(self._dist_graphs) >= 8:
+                self._dist_graphs.clear()
+            self._dist_graphs[key] = ent
+        ent[0].replay()
+        e.L.dm_launch_count_add(ent[1])
+        self._last_fg = ent[2]
+        return self._last_fg
 
     def run(self, labels_tile, feats_local, tau, *, image_tile=None, xs_local=None, ys_local_rel=None, max_rounds=64,
             gather_outputs=True, mlp=None):
@@ -325,7 +412,7 @@ class ShardedMergeEngine:
                 dist.all_reduce(self.mask_cnt, op=SUM, group=grp)
             self.flags.zero_()
             L.check(L.dm_shard_frontier(_p(self.mask_cnt), _p(self.cnt_local), R, _p(e.cnt), _p(self.send), s), "dm_shard_frontier")
-            self._exchange_rows(self.send, add=True)
+            self._exchange_rows(self.send, add=True, buf=0)
             # (4) merge loop on the tile's edges with the replicated parent array
             e.parent.copy_(e.iota)
             e.alive.fill_(1)
@@ -335,31 +422,8 @@ class ShardedMergeEngine:
                 raise ValueError("the pair-MLP takes concat(mean[lo], mean[hi]): in_features must be 2 D")
             e._score(mlp, None)
             rounds = merges = 0
+            fg = self._last_fg = self._pre_exchange(tau, mlp, max_rounds > 0, True, 0)
             while True:
-                if mlp is None:
-                    L.check(L.dm_merge_select_l2(_p(e.scores), float(tau), _p(n_edges), cap, _p(e.selected),
-                                                 e.counts[4:5].data_ptr(), s), "dm_merge_select_l2")
-                else:
-                    L.check(L.dm_merge_select_mlp(_p(e.logits), mlp.n_out, _p(n_edges), cap, _p(e.selected),
-                                                  e.counts[4:5].data_ptr(), s), "dm_merge_select_mlp")
-                # Union-find of the round, prepared BEFORE anyone knows whether the round takes place: local unions, then the
-                # frontier pairs (shared component, its local root).  The pairs of all ranks carry the whole cross-tile
-                # connectivity -- no iteration, no convergence test -- and the round's flags ("edges selected", errors)
-                # travel in the same slot: ONE exchange per round.  (Nothing selected anywhere: no unions, no pairs.)
-                if rounds < max_rounds:
-                    L.check(L.dm_uf_union(_p(e.parent), _p(e.keys), _p(e.selected), _p(n_edges), cap, s), "dm_uf_union")
-                    L.check(L.dm_uf_compress(_p(e.parent), R, s), "dm_uf_compress")
-                    L.check(L.dm_shard_frontier_pairs(_p(e.parent), _p(e.alive), _p(self.mask), self.rank, R, _p(self.fslot),
-                                                      self.row_cap, s), "dm_shard_frontier_pairs")
-                else:
-                    self.fslot[:16].zero_()
-                # the round's flags (edges selected; first round: this rank's tile-pass conditions) -> the slot header
-                L.check(L.dm_shard_round_flags(_p(e.counts), _p(self.flags), int(rounds == 0), _p(self.fslot_flags), s),
-                        "dm_shard_round_flags")
-                if self.peer_pairs is not None:                     # one kernel of NVLink peer stores + a barrier
-                    fg = self.peer_pairs.exchange(L, self.fslot, self.rank, 80, (80, 8), (80, 0), self.row_cap, s)
-                else:
-                    fg = all_gather_slots(self.fslot, dist, grp).view(self.world, self.fslot_bytes)
                 hf, c = self._read_headers(fg)
                 f = [max(int(h[2 + k]) for h in hf) for k in range(8)]     # every rank sees every rank's flags: all act alike
                 if f[4] != 0:
@@ -372,29 +436,7 @@ class ShardedMergeEngine:
                 if f[0] == 0 or rounds == max_rounds:
                     break
                 rounds += 1
-                L.check(L.dm_uf_union_slots(_p(e.parent), _p(fg), self.world, self.fslot_bytes, self.row_cap, R, s),
-                        "dm_uf_union_slots")
-                L.check(L.dm_uf_compress(_p(e.parent), R, s), "dm_uf_compress")
-                if self.peer_parent is not None:                   # fills in the regions this rank does not see
-                    self.peer_parent.all_reduce(L, 1, s)
-                else:
-                    dist.all_reduce(e.parent, op=MIN, group=grp)
-                # rows of components that grew across a tile border go to every rank that now sees them
-                self.mask_old.copy_(self.mask)
-                L.check(L.dm_shard_propagate(_p(e.parent), _p(e.alive), _p(self.mask), _p(self.grew), R, s), "dm_shard_propagate")
-                L.check(L.dm_shard_plan(_p(e.parent), _p(e.alive), _p(self.mask_old), _p(self.mask), _p(self.grew), self.rank, R,
-                                        _p(self.send), _p(self.seen_comp), s), "dm_shard_plan")
-                self._exchange_rows(self.send, add=False)
-                e.side.wait_stream(cur)                            # merged statistics beside the edge re-keying (as on one GPU)
-                with torch.cuda.stream(e.side):
-                    L.check(L.dm_merge_apply_masked(_p(e.parent), _p(e.alive), _p(e.changed), _p(e.sum), _p(e.cnt), _p(e.area),
-                                                    _p(e.perim), R, D, e.counts[5:6].data_ptr(), _p(self.seen_comp),
-                                                    _p(e.ws_side), e.ws_side_bytes, _stream()), "dm_merge_apply_masked")
-                L.check(L.dm_edges_rekey(_p(e.parent), _p(e.keys), _p(e.blen), _p(e.scores), _p(n_edges), cap, R, _p(e.perim),
-                                         _p(e.ws), e.ws_bytes, s), "dm_edges_rekey")
-                cur.wait_stream(e.side)
-                L.check(L.dm_region_mean(_p(e.sum), _p(e.cnt), R, D, _p(e.mean), _p(e.norm2), _p(e.changed), s), "dm_region_mean")
-                e._score(mlp, e.changed)
+                fg = self._dist_round(tau, mlp, rounds < max_rounds)
             # (5) tile-local relabel with the replicated root LUT
             L.check(L.dm_relabel(_p(labels_tile), self.rows_own, self.W, labels_tile.stride(0), _p(e.parent), R, _p(e.out),
                                  self.W, s), "dm_relabel")
