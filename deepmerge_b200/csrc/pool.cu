@@ -53,7 +53,8 @@ template <int K>
 __global__ void __launch_bounds__(256) pool_points_kernel(const int64_t* __restrict__ offsets,
                                                           const int32_t* __restrict__ ids, const float* __restrict__ feats,
                                                           int64_t ld, int64_t R_all, int D, int d_base, float* __restrict__ sum,
-                                                          int32_t* __restrict__ cnt, const int64_t* __restrict__ range) {
+                                                          int32_t* __restrict__ cnt, const int64_t* __restrict__ range,
+                                                          float* __restrict__ mean, float* __restrict__ norm2) {
     const int lane = threadIdx.x & 31;
     // range (row tiles of a sharded scene: ids are global, the tile's points fall into a small id interval): only
     // regions [range[0], range[1]] are visited; rows and counts outside are the caller's
@@ -120,6 +121,22 @@ __global__ void __launch_bounds__(256) pool_points_kernel(const int64_t* __restr
         for (int k = 0; k < K; ++k)
             if (d_base + lane + 32 * k < D) sum[r * D + d_base + lane + 32 * k] = acc[k];
         if (lane == 0 && d_base == 0) cnt[r] = (int32_t)(b - a);
+        if (mean) {     // D <= 128: the whole row is in this pass -- mean and norm exactly as region_mean_kernel forms them
+            const int n = (int)(b - a);
+            const float c = n > 0 ? (float)n : __int_as_float(0x7fc00000);
+            float n2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (lane + 32 * k < D) {
+                    const float v = n > 0 ? __fdiv_rn(acc[k], c) : c;
+                    mean[r * D + lane + 32 * k] = v;
+                    n2 = __fmaf_rn(v, v, n2);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+            if (lane == 0) norm2[r] = n2;
+        }
         r = rn;
         a = an;
         b = bn;
@@ -409,8 +426,9 @@ extern "C" int dm_csr_build(const int32_t* rop, int64_t n, int64_t R, int64_t* o
 
 template <int K>
 static void launch_pool_points(const int64_t* offsets, const int32_t* ids, const float* feats, int64_t ld, int64_t R,
-                               int D, int d_base, float* sum, int32_t* cnt, const int64_t* range, cudaStream_t s) {
-    DM_COUNT_LAUNCH(); pool::pool_points_kernel<K><<<pool::grid_for(R * 32, 256, 8), 256, 0, s>>>(offsets, ids, feats, ld, R, D, d_base, sum, cnt, range);
+                               int D, int d_base, float* sum, int32_t* cnt, const int64_t* range, cudaStream_t s,
+                               float* mean = nullptr, float* norm2 = nullptr) {
+    DM_COUNT_LAUNCH(); pool::pool_points_kernel<K><<<pool::grid_for(R * 32, 256, 8), 256, 0, s>>>(offsets, ids, feats, ld, R, D, d_base, sum, cnt, range, mean, norm2);
 }
 
 extern "C" int dm_pool_points_csr_tile(const int64_t* offsets, const int32_t* ids, const float* feats, int64_t ld, int64_t R,
@@ -427,6 +445,21 @@ extern "C" int dm_pool_points_csr_tile(const int64_t* offsets, const int32_t* id
         else if (rem > 32) launch_pool_points<2>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, region_range, s);
         else launch_pool_points<1>(offsets, ids, feats, ld, R, (int)D, d0, sum, cnt, region_range, s);
     }
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_points_csr_mean(const int64_t* offsets, const int32_t* ids, const float* feats, int64_t ld, int64_t R,
+                                       int64_t D, float* sum, int32_t* cnt, float* mean, float* norm2, dm_stream_t stream) {
+    if (R < 0 || D <= 0 || ld < D) return DM_ERR_BAD_ARG;
+    if (D > 128) return DM_ERR_UNSUPPORTED;                 // the row must fit one pass of the pooling kernel
+    if (R == 0) return DM_OK;
+    if (!offsets || !sum || !cnt || !mean || !norm2) return DM_ERR_BAD_ARG;
+    cudaStream_t s = S(stream);
+    if (D > 96) launch_pool_points<4>(offsets, ids, feats, ld, R, (int)D, 0, sum, cnt, nullptr, s, mean, norm2);
+    else if (D > 64) launch_pool_points<3>(offsets, ids, feats, ld, R, (int)D, 0, sum, cnt, nullptr, s, mean, norm2);
+    else if (D > 32) launch_pool_points<2>(offsets, ids, feats, ld, R, (int)D, 0, sum, cnt, nullptr, s, mean, norm2);
+    else launch_pool_points<1>(offsets, ids, feats, ld, R, (int)D, 0, sum, cnt, nullptr, s, mean, norm2);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

@@ -510,7 +510,8 @@ class MergeEngine:
         L.check(L.dm_perimeter(_p(self.keys), _p(self.blen), _p(self.counts), self.cap, _p(self.border), _p(self.perim),
                                self.R, s), "dm_perimeter")
 
-    def _pool(self, labels, xs, ys, region_of_point, feats):
+    def _pool(self, labels, xs, ys, region_of_point, feats, with_mean=False):
+        """membership -> CSR -> per-region sums (-> means and norms in the same pass when with_mean and D <= 128)"""
         L, s = self.L, _stream()
         N = feats.shape[0]
         if N > self.N:
@@ -521,6 +522,12 @@ class MergeEngine:
             region_of_point = self.rop
         L.check(L.dm_csr_build(_p(region_of_point), N, self.R, _p(self.offsets), _p(self.pids), _p(self.ws_pool),
                                self.ws_pool_bytes, s), "dm_csr_build")
+        if with_mean and not self.pool_id_range and self.D <= 128 and os.environ.get("DM_POOL_MEAN", "1") != "0":
+            L.check(L.dm_pool_points_csr_mean(_p(self.offsets), _p(self.pids), _p(feats), feats.stride(0), self.R, self.D,
+                                              _p(self.sum), _p(self.cnt), _p(self.mean), _p(self.norm2), s),
+                    "dm_pool_points_csr_mean")
+            self._means_fresh = True
+            return
         rng = None
         if self.pool_id_range:          # a row tile's engine: only the id interval that holds the tile's points is visited
             if self.id_range is None:
@@ -580,8 +587,9 @@ class MergeEngine:
                 self.side.wait_stream(cur)
                 with torch.cuda.stream(self.side):
                     self._merge_init()
-                    self._pool(labels, xs, ys, region_of_point, feats)
-                    self._mean_all()
+                    self._pool(labels, xs, ys, region_of_point, feats, with_mean=True)
+                    if not self._means_fresh:
+                        self._mean_all()
                 self._rag(labels, image, rows_own, top_border, bottom_border)
                 cur.wait_stream(self.side)
                 try:

@@ -164,6 +164,11 @@ int dm_pool_points_csr_tile(const int64_t* offsets, const int32_t* point_ids, co
                             dm_stream_t stream);
 int dm_points_id_range(const int32_t* region_of_point, int64_t n_points, int64_t n_regions, int64_t* range,
                        dm_stream_t stream);
+/* dm_pool_points_csr followed by dm_region_mean(only = NULL) in one pass over the points (D <= 128, else
+ * DM_ERR_UNSUPPORTED): the same sum, cnt, mean and norm2, bit for bit. */
+int dm_pool_points_csr_mean(const int64_t* offsets, const int32_t* point_ids, const float* feats, int64_t feat_ld,
+                            int64_t n_regions, int64_t D, float* sum, int32_t* cnt, float* mean, float* norm2,
+                            dm_stream_t stream);
 /* mean[r] = sum[r] / cnt[r] (IEEE fp32 division), norm2[r] = sum_d mean[r,d]^2.  A region without sample points
  * (cnt[r] == 0) gets mean = norm2 = NaN -- what np.mean over no rows gives -- so that its edges score NaN
  * (dm_score_l2) / NaN logits (dm_score_mlp_bf16) and are never selected by dm_merge_select_*.
