@@ -604,3 +604,32 @@ def test_rag_against_c_oracle_at_medium_size(cuda):
     r1 = oc.min_roots(R, (kk >> np.uint64(32)).astype(np.int32), (kk & np.uint64(0xFFFFFFFF)).astype(np.int32))
     if res.rounds == 1:
         assert np.array_equal(r1, root)
+
+
+@pytest.mark.parametrize("D", [7, 100, 128])
+def test_pool_points_with_means_in_one_pass(cuda, D):
+    """dm_pool_points_csr_mean = dm_pool_points_csr + dm_region_mean, bit for bit (sum, cnt, mean, norm2), including
+    regions without points (NaN mean and norm)."""
+    import torch
+    from deepmerge_b200 import raster as rs
+    from deepmerge_b200._lib import lib
+    L = lib()
+    rng = np.random.default_rng(D)
+    R, N = 5000, 17000
+    rop = rng.integers(0, R - 40, N).astype(np.int32)              # the last 40 regions stay empty
+    feats = rng.standard_normal((N, D)).astype(np.float32)
+    d_rop, d_f = T(rop, cuda), T(feats, cuda)
+    off, ids = rs.csr_from_region_of_point(d_rop, R)
+    s1, c1 = rs.pool_points_csr(off, ids, d_f)
+    m1, n1 = rs.region_mean(s1, c1)
+    s2 = torch.empty_like(s1); c2 = torch.empty_like(c1); m2 = torch.empty_like(m1); n2 = torch.empty_like(n1)
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(L.dm_pool_points_csr_mean(off.data_ptr(), ids.data_ptr(), d_f.data_ptr(), D, R, D, s2.data_ptr(), c2.data_ptr(),
+                                      m2.data_ptr(), n2.data_ptr(), st), "dm_pool_points_csr_mean")
+    torch.cuda.synchronize()
+    assert torch.equal(s1, s2) and torch.equal(c1, c2)
+    assert np.array_equal(m1.cpu().numpy(), m2.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(n1.cpu().numpy(), n2.cpu().numpy(), equal_nan=True)
+    assert np.isnan(m2[-40:].cpu().numpy()).all()
+    assert L.dm_pool_points_csr_mean(off.data_ptr(), ids.data_ptr(), d_f.data_ptr(), 200, R, 200, s2.data_ptr(), c2.data_ptr(),
+                                     m2.data_ptr(), n2.data_ptr(), st) == -4          # DM_ERR_UNSUPPORTED: D > 128
