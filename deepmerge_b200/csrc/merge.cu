@@ -233,8 +233,13 @@ __device__ __forceinline__ int lut(const int32_t* __restrict__ root, int l, int 
 }
 
 // 128-bit streaming loads/stores; the root LUT (4 B x R) stays in L2 / L1.
+// gate (may be null): the kernel does nothing when *gate != 0 -- a relabel enqueued BEFORE the host has read the merge
+// loop's last selection count runs only if that count is zero (no further round), so the loop's last read-back does not
+// leave the GPU idle.
 __global__ void __launch_bounds__(256) relabel_vec_kernel(const int4* __restrict__ in, int64_t n4,
-                                                          const int32_t* __restrict__ root, int R, int4* __restrict__ out) {
+                                                          const int32_t* __restrict__ root, int R, int4* __restrict__ out,
+                                                          const int64_t* __restrict__ gate) {
+    if (gate && *gate != 0) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + 3 * stride < n4; i += 4 * stride) {   // 4 independent 16-byte loads in flight per thread
@@ -261,7 +266,9 @@ __global__ void __launch_bounds__(256) relabel_vec_kernel(const int4* __restrict
 }
 
 __global__ void relabel_scalar_kernel(const int32_t* __restrict__ in, int64_t H, int64_t W, int64_t ld_in,
-                                      const int32_t* __restrict__ root, int R, int32_t* __restrict__ out, int64_t ld_out) {
+                                      const int32_t* __restrict__ root, int R, int32_t* __restrict__ out, int64_t ld_out,
+                                      const int64_t* __restrict__ gate) {
+    if (gate && *gate != 0) return;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t y = i / W, x = i - y * W;
         out[y * ld_out + x] = lut(root, in[y * ld_in + x], R);
@@ -811,8 +818,8 @@ extern "C" int dm_edges_rekey(const int32_t* parent, uint64_t* keys, uint32_t* l
     return DM_OK;
 }
 
-extern "C" int dm_relabel(const int32_t* labels, int64_t H, int64_t W, int64_t ld_in, const int32_t* root, int64_t R,
-                          int32_t* out, int64_t ld_out, dm_stream_t stream) {
+extern "C" int dm_relabel_gated(const int32_t* labels, int64_t H, int64_t W, int64_t ld_in, const int32_t* root, int64_t R,
+                                int32_t* out, int64_t ld_out, const int64_t* skip_if_nonzero, dm_stream_t stream) {
     if (H < 0 || W < 0 || ld_in < W || ld_out < W || R < 0 || R > 0x7fffffff) return DM_ERR_BAD_ARG;
     if (H == 0 || W == 0) return DM_OK;
     if (!labels || !out || (!root && R > 0)) return DM_ERR_BAD_ARG;
@@ -823,12 +830,17 @@ extern "C" int dm_relabel(const int32_t* labels, int64_t H, int64_t W, int64_t l
         const int64_t n4 = n / 4;
         // 4 x 16 B per thread per trip; grid sized to a whole number of waves of the SM count
         const unsigned g = (unsigned)imax64(1, imin64(ceil_div(n4, 256 * 4), (int64_t)num_sms() * 8));
-        DM_COUNT_LAUNCH(); merge::relabel_vec_kernel<<<g, 256, 0, s>>>((const int4*)labels, n4, root, (int)R, (int4*)out);
+        DM_COUNT_LAUNCH(); merge::relabel_vec_kernel<<<g, 256, 0, s>>>((const int4*)labels, n4, root, (int)R, (int4*)out, skip_if_nonzero);
     } else {
-        DM_COUNT_LAUNCH(); merge::relabel_scalar_kernel<<<grid_for(n), 256, 0, s>>>(labels, H, W, ld_in, root, (int)R, out, ld_out);
+        DM_COUNT_LAUNCH(); merge::relabel_scalar_kernel<<<grid_for(n), 256, 0, s>>>(labels, H, W, ld_in, root, (int)R, out, ld_out, skip_if_nonzero);
     }
     DM_LAUNCH_CHECK();
     return DM_OK;
+}
+
+extern "C" int dm_relabel(const int32_t* labels, int64_t H, int64_t W, int64_t ld_in, const int32_t* root, int64_t R,
+                          int32_t* out, int64_t ld_out, dm_stream_t stream) {
+    return dm_relabel_gated(labels, H, W, ld_in, root, R, out, ld_out, nullptr, stream);
 }
 
 extern "C" size_t dm_compact_roots_workspace_bytes(int64_t R) {

@@ -543,9 +543,12 @@ class MergeEngine:
                 "dm_region_mean")
         self._means_fresh = True
 
-    def _read_counts(self):
+    def _read_counts(self, after_enqueue=None):
+        """The loop's host read-back; after_enqueue() is called between the enqueue of the copy and the wait for it."""
         self.host_counts.copy_(self.counts, non_blocking=True)
         self.done.record()
+        if after_enqueue is not None:
+            after_enqueue()
         self.done.synchronize()
         return self.host_counts.tolist()
 
@@ -592,18 +595,24 @@ class MergeEngine:
                         self._mean_all()
                 self._rag(labels, image, rows_own, top_border, bottom_border)
                 cur.wait_stream(self.side)
+                # The relabel is enqueued behind every selection, right AFTER the copy of the counters the host waits for and
+                # gated on the device by the selection's count: when the loop ends it is already running (no idle device
+                # during the last read-back), when it goes on the kernel returns at once.  The host never waits for it.
+                own = labels.shape[0] if rows_own is None else rows_own
+
+                def gated_relabel(force):
+                    self.L.check(self.L.dm_relabel_gated(_p(labels), own, self.W, labels.stride(0), _p(self.parent), self.R,
+                                                         _p(self.out), self.W, None if force else self.counts[4:5].data_ptr(),
+                                                         _stream()), "dm_relabel_gated")
+                gated = relabel and os.environ.get("DM_GATED_RELABEL", "1") != "0"
                 try:
-                    rounds, merges = self._merge_loop(tau, max_rounds, mlp)
+                    rounds, merges = self._merge_loop(tau, max_rounds, mlp, after_read=gated_relabel if gated else None)
+                    if relabel and not gated:
+                        gated_relabel(True)
                     break
                 except OverflowError as ov:            # raw edge list outgrew the capacity: resize, rerun
                     self.cap = int(ov.args[0]) + 1024
                     self._alloc()
-            if relabel:
-                # launched after the loop's last read-back, not gated behind the selection: in a stream of scenes the host
-                # prepares the next scene's launches while this kernel runs (measured: a gated launch costs 90 us / step)
-                own = labels.shape[0] if rows_own is None else rows_own
-                self.L.check(self.L.dm_relabel(_p(labels), own, self.W, labels.stride(0), _p(self.parent), self.R,
-                                               _p(self.out), self.W, _stream()), "dm_relabel")
             E = int(self.host_counts[0])
         return MergeResult(self.out[:labels.shape[0] if rows_own is None else rows_own] if relabel else None,
                            self.parent, rounds, merges, self.keys[:E], self.blen[:E], self.scores[:E], self.area,
@@ -635,7 +644,7 @@ class MergeEngine:
         self.counts[5:8].zero_()
         self._init_fresh = True
 
-    def _merge_loop(self, tau, max_rounds, mlp=None):
+    def _merge_loop(self, tau, max_rounds, mlp=None, after_read=None):
         L, s, R, D, cap = self.L, _stream(), self.R, self.D, self.cap
         n_edges = self.counts[0:1]
         if mlp is not None and mlp.in_features != 2 * D:
@@ -650,7 +659,7 @@ class MergeEngine:
         self._select(tau, mlp)
         rounds = merges = 0
         while True:
-            c = self._read_counts()
+            c = self._read_counts(None if after_read is None else (lambda: after_read(rounds == max_rounds)))
             if rounds == 0:
                 if c[3] == 1:
                     raise ValueError("labels contain ids >= n_regions")

@@ -286,6 +286,11 @@ int dm_edges_rekey(const int32_t* parent, uint64_t* edge_keys, uint32_t* boundar
                    void* ws, size_t ws_bytes, dm_stream_t stream);
 int dm_relabel(const int32_t* labels, int64_t H, int64_t W, int64_t ld_in, const int32_t* root,
                int64_t n_regions, int32_t* labels_out, int64_t ld_out, dm_stream_t stream);
+/* The same, enqueued before the host knows whether the merge loop goes on: the kernel does nothing when
+ * *skip_if_nonzero != 0 (device memory: the count of edges the last selection picked; NULL = dm_relabel).  The loop's last
+ * read-back then does not leave the device idle. */
+int dm_relabel_gated(const int32_t* labels, int64_t H, int64_t W, int64_t ld_in, const int32_t* root, int64_t n_regions,
+                     int32_t* out, int64_t ld_out, const int64_t* skip_if_nonzero, dm_stream_t stream);
 /* compact[r] = rank of root(r) among roots (ascending); n_roots_dev[0] = number of roots. */
 size_t dm_compact_roots_workspace_bytes(int64_t n_regions);
 int dm_compact_roots(const int32_t* root, int64_t n_regions, int32_t* compact, int64_t* n_roots_dev,

@@ -9,10 +9,11 @@ from deepmerge_b200.synth import CASCADE_TAU, cascade_feats, synth_scene
 side = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 cascade = len(sys.argv) > 3 and sys.argv[3] == "cascade"
+rmul = int(sys.argv[4]) if len(sys.argv) > 4 else 1      # engine sized for rmul x the regions (ids of other row tiles)
 dev = torch.device("cuda:0")
 sc = synth_scene(side, side, int(100000 * side * side / 1e8), C=4, device=dev)
 feats, tau = (cascade_feats(sc), CASCADE_TAU) if cascade else (sc.feats, 0.5)
-eng = MergeEngine(side, side, sc.n_regions, 100, C=4, n_points=sc.feats.shape[0], device=dev)
+eng = MergeEngine(side, side, sc.n_regions * rmul, 100, C=4, n_points=sc.feats.shape[0], device=dev)
 for _ in range(3):
     r = eng.run(sc.labels, feats, tau, image=sc.image, xs=sc.xs, ys=sc.ys)
 torch.cuda.synchronize()
