@@ -513,6 +513,22 @@ __global__ void slots_overflow_kernel(const unsigned char* __restrict__ slots, i
     if (over) *flag = 1;
 }
 
+// out = max over the slots of the int64 word at word_offset bytes of every slot (e.g. "edges selected" of every rank)
+__global__ void slots_word_max_kernel(const unsigned char* __restrict__ slots, int n_slots, int64_t slot_bytes,
+                                      int64_t word_offset, int64_t* __restrict__ out) {
+    long long m = 0;
+    for (int g = threadIdx.x; g < n_slots; g += blockDim.x) {
+        const long long v = *(const long long*)(slots + (size_t)g * slot_bytes + word_offset);
+        m = v > m ? v : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long v = __shfl_xor_sync(0xffffffffu, m, o);
+        m = v > m ? v : m;
+    }
+    if (threadIdx.x == 0) *out = m;
+}
+
 __global__ void any_diff_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int64_t n,
                                 int64_t* __restrict__ flag) {
     bool d = false;
@@ -616,6 +632,18 @@ extern "C" int dm_slots_overflow(const void* slots, int64_t n_slots, int64_t slo
     if (!slots) return DM_ERR_BAD_ARG;
     DM_COUNT_LAUNCH(); merge::slots_overflow_kernel<<<1, 64, 0, S(stream)>>>((const unsigned char*)slots, (int)n_slots, slot_bytes, capacity,
                                                                        flag_dev);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_slots_word_max(const void* slots, int64_t n_slots, int64_t slot_bytes, int64_t word_offset, int64_t* out_dev,
+                                 dm_stream_t stream) {
+    if (n_slots < 0 || n_slots > 4096 || slot_bytes < 8 || word_offset < 0 || (word_offset & 7) || word_offset + 8 > slot_bytes ||
+        !out_dev)
+        return DM_ERR_BAD_ARG;
+    if (n_slots > 0 && !slots) return DM_ERR_BAD_ARG;
+    DM_COUNT_LAUNCH(); merge::slots_word_max_kernel<<<1, 32, 0, S(stream)>>>((const unsigned char*)slots, (int)n_slots, slot_bytes, word_offset,
+                                                                       out_dev);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

@@ -240,6 +240,7 @@ class ShardedMergeEngine:
                 self.peer_error = repr(ex)
         e.sum.zero_()                                              # rows the pooling pass never writes start as zeros
         self._dist_graphs, self._last_fg = {}, None
+        self.any_selected = z(1, dt=torch.int64)
         self.host_fflags = torch.zeros((self.world, 10), dtype=torch.int64).pin_memory()
         self.hdr_dev = z(self.world, 80, dt=torch.uint8)
         self.host_flags = torch.zeros(8, dtype=torch.int64).pin_memory()
@@ -269,14 +270,16 @@ class ShardedMergeEngine:
         else:         # whole rows from their single sender: one launch for all slots
             L.check(L.dm_rows_unpack_slots(_p(g), self.world, self.slot_bytes, rc, e.R, e.D, _p(e.sum), 0, s), "dm_rows_unpack_slots")
 
-    def _read_headers(self, gathered):
+    def _read_headers(self, gathered, after_enqueue=None):
         """The round's one host read-back: the slot headers of all ranks ([count, pad, 8 flags] each) and this rank's
-        engine counters."""
+        engine counters.  after_enqueue() runs between the enqueue of the copies and the wait for them."""
         e = self.eng
         self.hdr_dev.copy_(gathered[:, :80])                       # one strided copy of the headers, then one to the host
         self.host_fflags.copy_(self.hdr_dev.view(torch.int64).view(self.world, 10), non_blocking=True)
         e.host_counts.copy_(e.counts, non_blocking=True)
         e.done.record()
+        if after_enqueue is not None:
+            after_enqueue()
         e.done.synchronize()
         return self.host_fflags.tolist(), e.host_counts.tolist()
 
@@ -302,8 +305,12 @@ class ShardedMergeEngine:
         L.check(L.dm_shard_round_flags(_p(e.counts), _p(self.flags), int(first_round), _p(self.fslot_flags), s),
                 "dm_shard_round_flags")
         if self.peer_pairs is not None:                     # one kernel of NVLink peer stores + a barrier
-            return self.peer_pairs.exchange(L, self.fslot, self.rank, 80, (80, 8), (80, 0), self.row_cap, s, buf)
-        return all_gather_slots(self.fslot, self.dist, self.group).view(self.world, self.fslot_bytes)
+            fg = self.peer_pairs.exchange(L, self.fslot, self.rank, 80, (80, 8), (80, 0), self.row_cap, s, buf)
+        else:
+            fg = all_gather_slots(self.fslot, self.dist, self.group).view(self.world, self.fslot_bytes)
+        # "did any rank select an edge" on the device: the gate of the relabel that follows the read-back's copy
+        L.check(L.dm_slots_word_max(_p(fg), self.world, self.fslot_bytes, 16, _p(self.any_selected), s), "dm_slots_word_max")
+        return fg
 
     def _dist_round_body(self, tau, mlp, do_unions, fg):
         """One round between two read-backs: unions from everybody's frontier pairs, rows of the components that grew
@@ -423,8 +430,15 @@ class ShardedMergeEngine:
             e._score(mlp, None)
             rounds = merges = 0
             fg = self._last_fg = self._pre_exchange(tau, mlp, max_rounds > 0, True, 0)
+            # (5) tile-local relabel with the replicated root LUT: enqueued behind every exchange, right after the copies the
+            #     host waits for, and gated on the device by "no rank selected an edge" -- when the loop ends it is already
+            #     running, when it goes on the kernel returns at once
+            def gated_relabel():
+                L.check(L.dm_relabel_gated(_p(labels_tile), self.rows_own, self.W, labels_tile.stride(0), _p(e.parent), R,
+                                           _p(e.out), self.W, None if rounds == max_rounds else _p(self.any_selected), s),
+                        "dm_relabel_gated")
             while True:
-                hf, c = self._read_headers(fg)
+                hf, c = self._read_headers(fg, gated_relabel)
                 f = [max(int(h[2 + k]) for h in hf) for k in range(8)]     # every rank sees every rank's flags: all act alike
                 if f[4] != 0:
                     raise ValueError("labels contain ids >= n_regions")
@@ -437,9 +451,6 @@ class ShardedMergeEngine:
                     break
                 rounds += 1
                 fg = self._dist_round(tau, mlp, rounds < max_rounds)
-            # (5) tile-local relabel with the replicated root LUT
-            L.check(L.dm_relabel(_p(labels_tile), self.rows_own, self.W, labels_tile.stride(0), _p(e.parent), R, _p(e.out),
-                                 self.W, s), "dm_relabel")
             Ef = int(e.host_counts[0])
             if gather_outputs:
                 # per-tile partials -> global statistics; tile edge lists -> the global final edge list

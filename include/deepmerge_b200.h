@@ -356,6 +356,10 @@ int dm_peer_allreduce_i32(const void* peer_bases_dev, int64_t world, int64_t ran
 int dm_shard_round_flags(const int64_t* counts, int64_t* flags, int first_round, int64_t* slot_flags, dm_stream_t stream);
 int dm_slots_overflow(const void* slots, int64_t n_slots, int64_t slot_bytes, int64_t capacity, int64_t* flag_dev,
                       dm_stream_t stream);
+/* *out_dev = max over the gathered slots of the (non-negative) int64 word at word_offset of every slot -- "did any rank
+ * select an edge", computed where dm_relabel_gated can read it. */
+int dm_slots_word_max(const void* slots, int64_t n_slots, int64_t slot_bytes, int64_t word_offset, int64_t* out_dev,
+                      dm_stream_t stream);
 int dm_peer_put_slot(const void* slot, const int64_t* peer_bases_dev, int64_t world, int64_t rank, int64_t slot_bytes,
                      int64_t header_bytes, int64_t seg0_offset, int64_t seg0_elem_bytes, int64_t seg1_offset,
                      int64_t seg1_elem_bytes, int64_t capacity, dm_stream_t stream);
