@@ -1217,7 +1217,8 @@ int sort_unique(uint64_t* keys, uint32_t* vals, const int64_t* n_dev, int64_t ca
             H.deg = hw.deg; H.off = hw.off; H.cur = hw.cur; H.chunk_tot = hw.chunk_tot; H.hubs = hw.hubs; H.misc = hw.misc;
             H.t_ent = hw.t_ent; H.t_bkt = hw.t_bkt;
             H.n_ids = n_ids;
-            const int grid = (int)imax64(1, imin64(ceil_div(imax64(cap, n_ids), SORT_THREADS * 4), hlimit));
+            static const int grid_cap = getenv("DM_HASH_GRID") ? atoi(getenv("DM_HASH_GRID")) : 1 << 30;   // experiments
+            const int grid = (int)imax64(1, imin64(imin64(ceil_div(imax64(cap, n_ids), SORT_THREADS * 4), hlimit), grid_cap));
             DM_CUDA(cudaMemsetAsync(A.bar, 0, 2 * sizeof(unsigned), s));
             DM_CUDA(cudaMemsetAsync(H.misc, 0, 4 * sizeof(unsigned), s));
             void* args[] = {(void*)&H};
