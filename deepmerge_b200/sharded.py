@@ -544,7 +544,7 @@ def position_checksum(t, first=0, chunk=1 << 24):
     return int(acc.item())
 
 
-def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks):
+def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks, emit=True):
     """Weak scaling: every rank owns a tile of H_1 x W_1 / ... -- the N-GPU scene is the single-GPU
     workload's height times N (same tile per GPU), so per-GPU work is fixed as N grows."""
     import numpy as np
@@ -700,6 +700,7 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
             torch.cuda.empty_cache()
         except torch.OutOfMemoryError:
             parity_note = "skipped: the whole scene does not fit one GPU beside this rank's tile"
+    line = None
     if rank == 0:
         peak, kind = measured_peaks()
         alg = (4 + C) * rows_t * W + 12 * (3 * R // world) + 16 * (R // world) * C
@@ -710,8 +711,8 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
             "scaling": "strong" if fixed_scene else "weak", "vs_baseline": None, "dtype": "int32/u8 index + fp32 scores",
             "data": "synthetic",
             "config": {"workload": (SHARDED_WORKLOAD if fixed_scene else
-                                    f"{workload1} -- one such tile per GPU, stacked by rows ({H}x{W}), row-tile sharded with "
-                                    "NCCL edge-list all-gather + region-statistics all-reduce"),
+                                    f"{workload1} -- one such tile per GPU, stacked by rows ({H}x{W}), row-tile sharded: frontier "
+                                    "exchange, peer-store slots and peer all-reduce over NVLink symmetric memory"),
                        "H": H, "W": W, "bands": C, "segments": R,
                        "points": int(sc.xs.shape[0]), "embed_dim": D, "tau": cfg["tau"], "parallelism": f"row-tiles x{world}",
                        "result_form": "distributed (tile label maps, replicated root LUT, per-rank partial region statistics and "
@@ -730,11 +731,14 @@ def bench_sharded(args, cfg1, workload1, dist, dev, ClockSampler, measured_peaks
                     "note": "copy_only_* = pinned host <-> device copies of the same buffers with every rank copying at the same "
                             "time and nothing else running (slowest rank): the host side's ceiling for this step"},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "rag_pool_kernel (fused RAG + band pooling raster pass), rank 0's tile", "bound": "hbm",
+            "roofline": {"kernel": "rag_blocks_kernel (fused RAG + band pooling raster pass), rank 0's tile", "bound": "hbm",
                          "achieved": alg / (rag_ms * 1e-3) / 1e9, "peak": peak, "peak_kind": kind, "unit": "GB/s",
                          "frac": alg / (rag_ms * 1e-3) / 1e9 / peak, "ms": rag_ms, "algorithmic_bytes": alg, "traffic": None},
             "cpu_baseline": None, "clocks": clocks.summary(),
         }
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
     dist.barrier()
-    dist.destroy_process_group()
+    if emit:
+        dist.destroy_process_group()
+    return line if rank == 0 else None
