@@ -527,7 +527,7 @@ class ShardedMergeEngine:
 # bench leg for N > 1 (launched by torchrun, one rank per GPU)
 # ----------------------------------------------------------------------------------------------
 SHARDED_CFG = dict(H=40000, W=40000, R=1000000, C=4, P=4, D=100, tau=0.5, seed=1234)
-SHARDED_WORKLOAD = "configs[2]: 40k x 40k scene, ~1M segments, row-tile sharded across N B200 with NCCL boundary exchange"
+SHARDED_WORKLOAD = "configs[2]: 40k x 40k scene, ~1M segments, row-tile sharded across N B200 (frontier exchange and peer all-reduce over NVLink symmetric memory)"
 
 
 def position_checksum(t, first=0, chunk=1 << 24):
