@@ -68,6 +68,20 @@ def test_bad_arguments_are_rejected_without_cuda(L):
     assert L.dm_resize_area(None, 4, 50, 32, 0, None, None, None, None) == bad        # mode 0 needs an integer factor
     assert L.dm_resize_area(None, 4, 50, 32, 1, None, None, None, None) == bad        # tables / buffers missing
     assert L.dm_resize_area(None, 0, 64, 32, 0, None, None, None, None) == 0          # nothing to do
+    # entry points added in round 2
+    assert L.dm_relabel_gated(None, 4, 4, 2, None, 4, None, 4, None, None) == bad     # pitch < width
+    assert L.dm_relabel_gated(None, 0, 4, 4, None, 0, None, 4, None, None) == 0
+    assert L.dm_pool_points_csr_mean(None, None, None, 200, 5, 200, None, None, None, None, None) == _lib.DM_ERR_UNSUPPORTED
+    assert L.dm_pool_points_csr_mean(None, None, None, 3, 5, 100, None, None, None, None, None) == bad   # ld < D
+    assert L.dm_pool_points_csr_tile(None, None, None, 100, 5, 100, None, None, None, None) == bad       # null pointers
+    assert L.dm_peer_allreduce_i32(None, 2, 2, 0, 8, 0, None) == bad                  # rank outside the world
+    assert L.dm_peer_allreduce_i32(None, 2, 0, 0, 6, 0, None) == bad                  # n not a multiple of 4
+    assert L.dm_peer_allreduce_i32(None, 2, 0, 8, 8, 0, None) == bad                  # offset not a multiple of 16
+    assert L.dm_peer_allreduce_i32(None, 2, 0, 0, 8, 2, None) == bad                  # unknown op
+    assert L.dm_peer_allreduce_i32(None, 2, 0, 0, 0, 1, None) == 0                    # nothing to reduce
+    assert L.dm_slots_word_max(None, 2, 80, 12, None, None) == bad                    # unaligned word / no output
+    assert L.dm_region_bbox(None, 4, 4, 2, 3, None, None, None) == bad                # pitch < width
+    assert L.dm_points_id_range(None, -1, 3, None, None) == bad
     with pytest.raises(ValueError):
         L.check(bad, "x")
     with pytest.raises(RuntimeError):
