@@ -720,8 +720,12 @@ class MergeEngine:
         if ent is None:
             g = torch.cuda.CUDAGraph()
             n0 = self.L.dm_launch_count()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._round_body(tau, mlp)
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._round_body(tau, mlp)
+            except Exception:                      # capture refused (driver / library in use): plain launches from now on
+                self.use_graphs = False
+                return self._round_body(tau, mlp)
             ent = (g, self.L.dm_launch_count() - n0)
             if len(self._round_graphs) >= 8:
                 self._round_graphs.clear()

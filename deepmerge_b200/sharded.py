@@ -361,8 +361,13 @@ class ShardedMergeEngine:
         if ent is None:
             g = torch.cuda.CUDAGraph()
             n0 = e.L.dm_launch_count()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                out = self._dist_round_body(tau, mlp, do_unions, src)
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    out = self._dist_round_body(tau, mlp, do_unions, src)
+            except Exception:                      # capture refused: plain launches from now on (same kernels, same order)
+                e.use_graphs = False
+                self._last_fg = self._dist_round_body(tau, mlp, do_unions, src)
+                return self._last_fg
             ent = (g, e.L.dm_launch_count() - n0, out)
             if len(self._dist_graphs) >= 8:
                 self._dist_graphs.clear()
