@@ -114,8 +114,10 @@ rag_blocks_kernel(const __grid_constant__ CUtensorMap mapL, const __grid_constan
     // ---- this warp's run of units (unit = TH rows of one strip, column-major order) -------
     const long long total_units = (long long)P.tiles_x * P.tiles_y;
     const long long gw = (long long)blockIdx.x * CF::NWARPS + warp;
-    const long long u_begin = min(total_units, gw * (long long)P.tiles_per_cta);
-    const long long u_end = min(total_units, u_begin + P.tiles_per_cta);
+    // even split over all warps of the grid: runs differ by at most one unit, no SM is left without a CTA
+    const long long n_warps = (long long)gridDim.x * CF::NWARPS;
+    const long long u_begin = total_units / n_warps * gw + min(gw, total_units % n_warps);
+    const long long u_end = u_begin + total_units / n_warps + (gw < total_units % n_warps ? 1 : 0);
     const int my_units = (int)(u_end - u_begin);
 
     // ---- init (warp-private, no block barrier needed) ---------------------------------------
@@ -344,7 +346,7 @@ static int launch(const Params& Pin, bool allow_tma, cudaStream_t s) {
     const long long per = ceil_div(total, max_warps);
     if (per > 0x7fffffff) return DM_ERR_BAD_ARG;
     P.tiles_per_cta = (int)per;
-    const int grid = (int)ceil_div(ceil_div(total, per), CF::NWARPS);
+    const int grid = (int)imin64(num_sms(), ceil_div(total, CF::NWARPS));   // (a tiny raster: one unit per warp)
 
     CUtensorMap mapL, mapI;
     memset(&mapL, 0, sizeof(mapL));
