@@ -23,22 +23,32 @@ def main():
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for H, W, R, tau in ((260, 384, 500, 0.5), (1203, 1024, 5000, 0.5), (240, 384, 600, 30.0)):
+    # the last scene is the multi-round workload (three rounds: the captured round body is replayed, its exchange buffers
+    # are reused round after round); every scene is run twice by the same engine (graphs captured in the first run)
+    for H, W, R, tau in ((260, 384, 500, 0.5), (1203, 1024, 5000, 0.5), (240, 384, 600, 30.0), (600, 800, 4000, "cascade")):
         sc = o.synth_scene(H, W, R, C=4)
+        if tau == "cascade":
+            from deepmerge_b200.synth import CASCADE_TAU
+            sc["feats"] = o.synth_cascade_feats(sc["region_of_point"], sc["region_obj"], H, W, R)
+            tau = CASCADE_TAU
         n, D = sc["n_regions"], sc["feats"].shape[1]
         T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
         y0, y1 = tile_bounds(H, world, rank)
         last = rank == world - 1
         mine = points_in_tile(torch.from_numpy(sc["ys"]), y0, y1).numpy()
         eng = ShardedMergeEngine(H, W, n, D, 4, len(mine), dist, dev)
-        res = eng.run(T(sc["labels"][y0:y1 + (0 if last else 1)]), T(sc["feats"][mine]), tau, image_tile=T(sc["image"][y0:y1]),
-                      xs_local=T(sc["xs"][mine]), ys_local_rel=T(sc["ys"][mine] - y0), gather_outputs=True)
+        tile = (T(sc["labels"][y0:y1 + (0 if last else 1)]), T(sc["feats"][mine]))
+        kw = dict(image_tile=T(sc["image"][y0:y1]), xs_local=T(sc["xs"][mine]), ys_local_rel=T(sc["ys"][mine] - y0))
+        eng.run(*tile, tau, gather_outputs=False, **kw)
+        res = eng.run(*tile, tau, gather_outputs=True, **kw)
         cs = torch.tensor([position_checksum(res.labels, y0 * W), position_checksum(res.root), res.rounds, res.merges],
                           dtype=torch.int64, device=dev)
         every = [torch.zeros_like(cs) for _ in range(world)]
         dist.all_gather(every, cs)
         if rank == 0:
             want = o.merge_scene(sc["labels"], n, sc["region_of_point"], sc["feats"], tau=tau)
+            if (H, W, R) == (600, 800, 4000):
+                assert want["rounds"] == 3, want["rounds"]
             single = merge_scene(T(sc["labels"]), T(sc["feats"]), tau, n_regions=n, image=T(sc["image"]), xs=T(sc["xs"]),
                                  ys=T(sc["ys"]))
             assert np.array_equal(single.labels.cpu().numpy(), want["labels"])
